@@ -1,0 +1,331 @@
+"""ctypes binding of the C ABI in ``include/emcee_b200.h``.
+
+The shared library ``libemcee_b200.so`` is built in-tree by
+``__graft_entry__.build()`` (or ``make -C emcee_b200/csrc``).  There is no
+fallback: if the library is missing, or no CUDA device is visible when an
+engine is created, the caller gets an exception.
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["lib", "Engine", "EngineError", "device_count", "LIB_PATH", "EbMove"]
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libemcee_b200.so")
+
+EB_OK = 0
+EB_ERR_INVALID = -1
+EB_ERR_CUDA = -2
+EB_ERR_COMM = -3
+EB_ERR_STATE = -4
+EB_ERR_UNSUPPORTED = -5
+EB_ERR_NAN_LOGPROB = -10
+EB_ERR_INF_PARAM = -11
+EB_ERR_NAN_PARAM = -12
+EB_ERR_FEW_WALKERS = -13
+EB_ERR_NAN_INITIAL = -14
+
+EB_COMM_ID_BYTES = 128
+EB_IPC_BLOB_BYTES = 256
+EB_COMM_ALLGATHER = 0
+EB_COMM_P2P = 1
+
+MODEL_KINDS = {"gauss_iso": 0, "gauss_dense": 1, "rosenbrock": 2, "ring": 3}
+MOVE_KINDS = {"stretch": 0, "de": 1, "snooker": 2}
+
+
+class EbMove(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("nsplits", C.c_int32),
+        ("randomize_split", C.c_int32),
+        ("live_dangerously", C.c_int32),
+        ("weight", C.c_double),
+        ("p0", C.c_double),
+        ("p1", C.c_double),
+    ]
+
+
+class EngineError(RuntimeError):
+    """A failing C-ABI call that does not map onto one of the reference's own
+    exception types."""
+
+
+_dp = C.POINTER(C.c_double)
+_SIGNATURES = {
+    "eb_abi_version": (C.c_int, []),
+    "eb_device_count": (C.c_int, []),
+    "eb_create": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "eb_destroy": (C.c_int, [C.c_void_p]),
+    "eb_last_error": (C.c_char_p, [C.c_void_p]),
+    "eb_model_set": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_size_t]),
+    "eb_set_state": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "eb_get_state": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "eb_compute_log_prob": (C.c_int, [C.c_void_p, _dp, C.c_size_t, _dp]),
+    "eb_set_rng": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
+    "eb_get_rng": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "eb_step": (C.c_int, [C.c_void_p, C.POINTER(EbMove), C.c_size_t, C.c_uint64, C.POINTER(C.c_uint8)]),
+    "eb_step_store": (
+        C.c_int,
+        [C.c_void_p, C.POINTER(EbMove), C.c_size_t, C.c_uint64, C.c_uint64, _dp, _dp, _dp],
+    ),
+    "eb_get_naccepted": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "eb_reset_counters": (C.c_int, [C.c_void_p]),
+    "eb_last_step_timing": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_uint64)]),
+    "eb_debug_taps": (
+        C.c_int,
+        [C.c_void_p, C.POINTER(C.c_int64), _dp, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+    ),
+    "eb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "eb_last_kernel_name": (C.c_char_p, [C.c_void_p]),
+    "eb_microbench": (C.c_int, [C.c_int, C.c_int, _dp]),
+    "eb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "eb_host_free": (C.c_int, [C.c_void_p]),
+    "eb_comm_id": (C.c_int, [C.c_char_p]),
+    "eb_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    "eb_comm_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "eb_comm_import": (C.c_int, [C.c_void_p, C.c_char_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (loaded once; raises if it was not built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "emcee_b200: %s is missing -- build it with `python -c 'import "
+                "__graft_entry__ as g; g.build()'` or `make -C emcee_b200/csrc`. "
+                "There is no CPU fallback." % LIB_PATH
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def device_count():
+    return int(lib().eb_device_count())
+
+
+def microbench(what, warps_per_sm=16):
+    """TFLOP/s (what = 0 DFMA, 1..3 DMMA shapes) or GB/s (4 = HBM copy)."""
+    out = C.c_double()
+    rc = lib().eb_microbench(int(what), int(warps_per_sm), C.byref(out))
+    if rc != EB_OK:
+        raise EngineError("eb_microbench failed (%d)" % rc)
+    return float(out.value)
+
+
+class _PinnedOwner(object):
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            lib().eb_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked host memory (full-speed H2D / D2H)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    ptr = C.c_void_p()
+    rc = lib().eb_host_alloc(max(n, 1), C.byref(ptr))
+    if rc != EB_OK:
+        raise EngineError("eb_host_alloc(%d) failed" % n)
+    buf = (C.c_char * max(n, 1)).from_address(ptr.value)
+    buf._owner = _PinnedOwner(ptr)  # freed when the last array viewing `buf` dies
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def _as_dp(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != shape:
+        raise ValueError("incompatible input dimensions {0}".format(a.shape))
+    return a
+
+
+class Engine(object):
+    """Thin owner of one ``eb_ctx``.  Maps error codes onto the exception types
+    the reference raises for the same conditions (``ensemble.py:314-323,
+    357-358,476-479,550-551``; ``moves/red_blue.py:64-70``)."""
+
+    def __init__(self, nwalkers, ndim, seed, device=0):
+        self._h = C.c_void_p()
+        self.nwalkers, self.ndim = int(nwalkers), int(ndim)
+        rc = lib().eb_create(int(device), self.nwalkers, self.ndim, int(seed) & (2**64 - 1), C.byref(self._h))
+        if rc != EB_OK:
+            msg = lib().eb_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise (ValueError if rc == EB_ERR_INVALID else EngineError)(msg)
+
+    # -- plumbing -------------------------------------------------------------
+    def _check(self, rc):
+        if rc == EB_OK:
+            return
+        msg = lib().eb_last_error(self._h).decode()
+        if rc in (EB_ERR_INVALID, EB_ERR_NAN_LOGPROB, EB_ERR_INF_PARAM, EB_ERR_NAN_PARAM, EB_ERR_NAN_INITIAL):
+            raise ValueError(msg)
+        if rc == EB_ERR_UNSUPPORTED:
+            raise NotImplementedError(msg)
+        if rc == EB_ERR_FEW_WALKERS:
+            raise RuntimeError(msg)
+        raise EngineError("%s (eb_status %d)" % (msg, rc))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().eb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- model / state ----------------------------------------------------------
+    def set_model(self, kind, params):
+        params = _f64(np.asarray(params, dtype=np.float64).ravel())
+        self._check(lib().eb_model_set(self._h, MODEL_KINDS[kind], _as_dp(params), params.size))
+
+    def set_state(self, coords, log_prob=None):
+        coords = _f64(coords, (self.nwalkers, self.ndim))
+        lp = None if log_prob is None else _f64(log_prob, (self.nwalkers,))
+        self._check(lib().eb_set_state(self._h, _as_dp(coords), None if lp is None else _as_dp(lp)))
+
+    def get_state(self):
+        coords = np.empty((self.nwalkers, self.ndim), dtype=np.float64)
+        lp = np.empty(self.nwalkers, dtype=np.float64)
+        self._check(lib().eb_get_state(self._h, _as_dp(coords), _as_dp(lp)))
+        return coords, lp
+
+    def compute_log_prob(self, coords):
+        coords = _f64(coords)
+        if coords.shape[-1] != self.ndim:
+            raise ValueError("incompatible input dimensions {0}".format(coords.shape))
+        flat = coords.reshape(-1, self.ndim)
+        out = np.empty(flat.shape[0], dtype=np.float64)
+        self._check(lib().eb_compute_log_prob(self._h, _as_dp(flat), flat.shape[0], _as_dp(out)))
+        return out.reshape(coords.shape[:-1])
+
+    # -- rng -----------------------------------------------------------------
+    def set_rng(self, seed, step):
+        self._check(lib().eb_set_rng(self._h, int(seed) & (2**64 - 1), int(step)))
+
+    def get_rng(self):
+        seed, step = C.c_uint64(), C.c_uint64()
+        self._check(lib().eb_get_rng(self._h, C.byref(seed), C.byref(step)))
+        return int(seed.value), int(step.value)
+
+    # -- stepping ----------------------------------------------------------------
+    @staticmethod
+    def pack_moves(moves):
+        """``moves``: list of (descriptor dict, weight)."""
+        arr = (EbMove * len(moves))()
+        for k, (d, w) in enumerate(moves):
+            arr[k].kind = MOVE_KINDS[d["kind"]]
+            arr[k].nsplits = int(d["nsplits"])
+            arr[k].randomize_split = int(bool(d["randomize_split"]))
+            arr[k].live_dangerously = int(bool(d["live_dangerously"]))
+            arr[k].weight = float(w)
+            arr[k].p0 = float(d["p0"])
+            arr[k].p1 = float(d["p1"])
+        return arr
+
+    def step(self, moves, nsteps, want_accepted=True):
+        arr = self.pack_moves(moves)
+        acc = np.zeros(self.nwalkers, dtype=np.uint8) if want_accepted else None
+        self._check(
+            lib().eb_step(
+                self._h, arr, len(arr), int(nsteps),
+                None if acc is None else acc.ctypes.data_as(C.POINTER(C.c_uint8)),
+            )
+        )
+        return None if acc is None else acc.astype(bool)
+
+    def step_store(self, moves, nsteps, thin_by, chain, log_prob, accepted):
+        arr = self.pack_moves(moves)
+        assert chain.flags.c_contiguous and log_prob.flags.c_contiguous and accepted.flags.c_contiguous
+        assert chain.dtype == np.float64 and log_prob.dtype == np.float64 and accepted.dtype == np.float64
+        self._check(
+            lib().eb_step_store(
+                self._h, arr, len(arr), int(nsteps), int(thin_by),
+                _as_dp(chain), _as_dp(log_prob), _as_dp(accepted),
+            )
+        )
+
+    def naccepted(self):
+        out = np.zeros(self.nwalkers, dtype=np.uint64)
+        self._check(lib().eb_get_naccepted(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def reset_counters(self):
+        self._check(lib().eb_reset_counters(self._h))
+
+    def last_step_timing(self):
+        ms, n = C.c_double(), C.c_uint64()
+        self._check(lib().eb_last_step_timing(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def last_kernel_name(self):
+        return lib().eb_last_kernel_name(self._h).decode()
+
+    def set_option(self, name, value):
+        self._check(lib().eb_set_option(self._h, name.encode(), int(value)))
+
+    def debug_taps(self):
+        n = self.nwalkers
+        partners = np.empty((3, n), dtype=np.int64)
+        scalar = np.empty(n, dtype=np.float64)
+        u = np.empty(n, dtype=np.float64)
+        active = np.empty(n, dtype=np.int64)
+        cnt = C.c_int64()
+        i64 = C.POINTER(C.c_int64)
+        self._check(
+            lib().eb_debug_taps(
+                self._h, partners.ctypes.data_as(i64), _as_dp(scalar), _as_dp(u),
+                active.ctypes.data_as(i64), C.byref(cnt),
+            )
+        )
+        k = int(cnt.value)
+        return dict(partners=partners[:, :k], scalar=scalar[:k], u_accept=u[:k], active=active[:k])
+
+    # -- multi-GPU ---------------------------------------------------------------
+    @staticmethod
+    def comm_id():
+        buf = C.create_string_buffer(EB_COMM_ID_BYTES)
+        rc = lib().eb_comm_id(buf)
+        if rc != EB_OK:
+            raise EngineError("eb_comm_id failed (is libnccl.so.2 loadable?)")
+        return buf.raw
+
+    def comm_init(self, comm_id, rank, nranks, mode=EB_COMM_ALLGATHER):
+        assert len(comm_id) == EB_COMM_ID_BYTES
+        self._check(lib().eb_comm_init(self._h, comm_id, int(rank), int(nranks), int(mode)))
+
+    def comm_export(self):
+        buf = C.create_string_buffer(EB_IPC_BLOB_BYTES)
+        self._check(lib().eb_comm_export(self._h, buf))
+        return buf.raw
+
+    def comm_import(self, blobs):
+        self._check(lib().eb_comm_import(self._h, blobs))

@@ -1,0 +1,763 @@
+// C ABI of the engine (include/emcee_b200.h): context, host-side step loop,
+// state / model transfer, error mapping.  No torch, no CPU fallback.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "comm.h"
+#include "engine.cuh"
+
+using namespace eb;
+
+struct eb_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int64_t N = 0;
+  int D = 0;
+  uint64_t seed = 0, step = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  double* coords = nullptr;
+  double* logp = nullptr;
+  uint8_t* accepted = nullptr;
+  unsigned long long* nacc = nullptr;
+  int* status_dev = nullptr;
+  int* status_host = nullptr;  // pinned
+
+  ModelDev model{};
+  double* model_params = nullptr;
+  double* model_chol = nullptr;
+  bool have_model = false, have_state = false;
+
+  int32_t* order = nullptr;  // [table_cap, N]
+  size_t table_cap = 0;
+  StepInfo* info_dev = nullptr;
+  StepInfo* info_host = nullptr;  // pinned
+
+  double* scratch_x = nullptr;
+  double* scratch_lp = nullptr;
+  size_t scratch_rows = 0;
+
+  // pinned staging for eb_step_store
+  double* stage[2] = {nullptr, nullptr};
+  uint8_t* stage_acc[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+
+  bool debug = false;
+  int64_t* tap_partners = nullptr;
+  double* tap_scalar = nullptr;
+  double* tap_u = nullptr;
+  int64_t* tap_active = nullptr;
+  int64_t tap_count = 0;
+
+  // optional L2 flush between steps (benchmark hygiene): per-step event pairs
+  bool l2_flush = false;
+  void* flush_buf = nullptr;
+  size_t flush_bytes = (size_t)256 << 20;
+  std::vector<cudaEvent_t> ev_pool;
+
+  double last_ms = 0.0;
+  uint64_t last_launches = 0;
+  const char* last_kernel = "none";
+  bool allow_dmma = true;
+
+  Comm comm;  // multi-GPU (comm.h)
+
+  std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+#define FAIL(ctx, code, ...)                      \
+  do {                                            \
+    char _b[512];                                 \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);        \
+    (ctx)->err = _b;                              \
+    return (code);                                \
+  } while (0)
+
+#define CK(ctx, call)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      cudaGetLastError();                                                                  \
+      FAIL(ctx, EB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
+           __LINE__);                                                                      \
+    }                                                                                      \
+  } while (0)
+
+// map (and clear) the device status word to the reference's exceptions, in the
+// order compute_log_prob raises them (ensemble.py:476-479, 550-551)
+static int check_status(eb_ctx* c) {
+  const int f = *c->status_host;
+  if (f == 0) return EB_OK;
+  *c->status_host = 0;
+  cudaMemsetAsync(c->status_dev, 0, sizeof(int), c->st);
+  cudaStreamSynchronize(c->st);
+  if (f & FLAG_INF_PARAM) FAIL(c, EB_ERR_INF_PARAM, "At least one parameter value was infinite");
+  if (f & FLAG_NAN_PARAM) FAIL(c, EB_ERR_NAN_PARAM, "At least one parameter value was NaN");
+  FAIL(c, EB_ERR_NAN_LOGPROB, "Probability function returned NaN");
+}
+
+static int fetch_status(eb_ctx* c) {
+  CK(c, cudaMemcpyAsync(c->status_host, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  CK(c, cudaStreamSynchronize(c->st));
+  return check_status(c);
+}
+
+extern "C" {
+
+int eb_abi_version(void) { return EB_ABI_VERSION; }
+
+int eb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* eb_last_error(const eb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int eb_create(int device, int64_t nwalkers, int64_t ndim, uint64_t seed, eb_ctx** out) {
+  if (!out) return EB_ERR_INVALID;
+  *out = nullptr;
+  if (nwalkers < 2 || ndim < 1 || nwalkers > (int64_t)0x7fffffff || ndim > 16384) {
+    g_create_err = "eb_create: need 2 <= nwalkers < 2^31 and 1 <= ndim <= 16384";
+    return EB_ERR_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_create_err = std::string("eb_create: no CUDA device (") + cudaGetErrorString(e) +
+                   "); this engine has no CPU fallback";
+    return EB_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_err = "eb_create: device index out of range";
+    return EB_ERR_INVALID;
+  }
+  eb_ctx* c = new eb_ctx();
+  c->device = device;
+  c->N = nwalkers;
+  c->D = (int)ndim;
+  c->seed = seed;
+  auto fail = [&](const char* what, cudaError_t err) {
+    g_create_err = std::string("eb_create: ") + what + ": " + cudaGetErrorString(err);
+    eb_destroy(c);
+    return EB_ERR_CUDA;
+  };
+#define CC(call)                             \
+  do {                                       \
+    cudaError_t _e = (call);                 \
+    if (_e != cudaSuccess) return fail(#call, _e); \
+  } while (0)
+  CC(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CC(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  CC(cudaEventCreate(&c->ev0));
+  CC(cudaEventCreate(&c->ev1));
+  const size_t nd = (size_t)nwalkers * (size_t)ndim;
+  CC(cudaMalloc(&c->coords, nd * sizeof(double)));
+  CC(cudaMalloc(&c->logp, (size_t)nwalkers * sizeof(double)));
+  CC(cudaMalloc(&c->accepted, (size_t)nwalkers));
+  CC(cudaMalloc(&c->nacc, (size_t)nwalkers * sizeof(unsigned long long)));
+  CC(cudaMalloc(&c->status_dev, sizeof(int)));
+  CC(cudaMallocHost(&c->status_host, sizeof(int)));
+  *c->status_host = 0;
+  CC(cudaMemsetAsync(c->status_dev, 0, sizeof(int), c->st));
+  CC(cudaMemsetAsync(c->accepted, 0, (size_t)nwalkers, c->st));
+  CC(cudaMemsetAsync(c->nacc, 0, (size_t)nwalkers * sizeof(unsigned long long), c->st));
+  // split tables for a chunk of steps: <= 64 MiB, 1..512 steps
+  size_t cap = (64u << 20) / ((size_t)nwalkers * sizeof(int32_t));
+  cap = std::max<size_t>(1, std::min<size_t>(cap, 512));
+  c->table_cap = cap;
+  CC(cudaMalloc(&c->order, cap * (size_t)nwalkers * sizeof(int32_t)));
+  CC(cudaMalloc(&c->info_dev, cap * sizeof(StepInfo)));
+  CC(cudaMallocHost(&c->info_host, cap * sizeof(StepInfo)));
+  CC(cudaStreamSynchronize(c->st));
+#undef CC
+  *out = c;
+  return EB_OK;
+}
+
+int eb_destroy(eb_ctx* c) {
+  if (!c) return EB_OK;
+  cudaSetDevice(c->device);
+  comm_destroy(c->comm);
+  if (c->st) cudaStreamSynchronize(c->st);
+  cudaFree(c->coords);
+  cudaFree(c->logp);
+  cudaFree(c->accepted);
+  cudaFree(c->nacc);
+  cudaFree(c->status_dev);
+  cudaFreeHost(c->status_host);
+  cudaFree(c->model_params);
+  cudaFree(c->model_chol);
+  cudaFree(c->order);
+  cudaFree(c->info_dev);
+  cudaFreeHost(c->info_host);
+  cudaFree(c->scratch_x);
+  cudaFree(c->scratch_lp);
+  for (int k = 0; k < 2; ++k) {
+    cudaFreeHost(c->stage[k]);
+    cudaFreeHost(c->stage_acc[k]);
+    if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
+  }
+  cudaFree(c->flush_buf);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  cudaFree(c->tap_partners);
+  cudaFree(c->tap_scalar);
+  cudaFree(c->tap_u);
+  cudaFree(c->tap_active);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->st) cudaStreamDestroy(c->st);
+  cudaGetLastError();
+  delete c;
+  return EB_OK;
+}
+
+// ---- model -----------------------------------------------------------------
+// Lower Cholesky factor of the symmetric part of A, packed for the DMMA kernel
+// (dense_dmma.cu).  Returns false when A is not numerically positive definite.
+static bool cholesky_lower(const double* A, int D, std::vector<double>& L) {
+  L.assign((size_t)D * D, 0.0);
+  for (int j = 0; j < D; ++j) {
+    double d = 0.5 * (A[(size_t)j * D + j] + A[(size_t)j * D + j]);
+    for (int k = 0; k < j; ++k) d -= L[(size_t)j * D + k] * L[(size_t)j * D + k];
+    if (!(d > 0.0) || !isfinite(d)) return false;
+    const double ljj = sqrt(d);
+    L[(size_t)j * D + j] = ljj;
+    for (int i = j + 1; i < D; ++i) {
+      double s = 0.5 * (A[(size_t)i * D + j] + A[(size_t)j * D + i]);
+      for (int k = 0; k < j; ++k) s -= L[(size_t)i * D + k] * L[(size_t)j * D + k];
+      L[(size_t)i * D + j] = s / ljj;
+    }
+  }
+  return true;
+}
+
+int eb_model_set(eb_ctx* c, int kind, const double* params, size_t nparams) {
+  if (!c) return EB_ERR_INVALID;
+  CK(c, cudaSetDevice(c->device));
+  const size_t D = (size_t)c->D;
+  ModelDev m{};
+  m.kind = kind;
+  std::vector<double> host;
+  switch (kind) {
+    case EB_MODEL_GAUSS_ISO:
+      if (nparams != 0) FAIL(c, EB_ERR_INVALID, "gauss_iso takes no parameters");
+      break;
+    case EB_MODEL_GAUSS_DENSE:
+      if (nparams != D + D * D || !params)
+        FAIL(c, EB_ERR_INVALID, "gauss_dense takes mu[D] followed by A[D*D] (got %zu doubles)", nparams);
+      for (size_t k = 0; k < nparams; ++k)
+        if (!isfinite(params[k])) FAIL(c, EB_ERR_INVALID, "gauss_dense parameters must be finite");
+      host.assign(params, params + nparams);
+      break;
+    case EB_MODEL_ROSENBROCK:
+    case EB_MODEL_RING:
+      if (nparams != 2 || !params) FAIL(c, EB_ERR_INVALID, "model takes exactly 2 parameters");
+      if (kind == EB_MODEL_RING && !(params[1] > 0.0)) FAIL(c, EB_ERR_INVALID, "ring sigma must be > 0");
+      if (kind == EB_MODEL_ROSENBROCK && D < 2) FAIL(c, EB_ERR_INVALID, "rosenbrock needs ndim >= 2");
+      m.s0 = params[0];
+      m.s1 = params[1];
+      break;
+    default:
+      FAIL(c, EB_ERR_INVALID, "unknown model kind %d", kind);
+  }
+  CK(c, cudaStreamSynchronize(c->st));
+  cudaFree(c->model_params);
+  cudaFree(c->model_chol);
+  c->model_params = nullptr;
+  c->model_chol = nullptr;
+  if (!host.empty()) {
+    CK(c, cudaMalloc(&c->model_params, host.size() * sizeof(double)));
+    CK(c, cudaMemcpy(c->model_params, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice));
+    m.params = c->model_params;
+    if (kind == EB_MODEL_GAUSS_DENSE && dense_dmma_supported(c->D)) {
+      std::vector<double> L;
+      if (cholesky_lower(host.data() + D, c->D, L)) {
+        std::vector<double> packed(dense_dmma_factor_doubles(c->D));
+        dense_dmma_pack_factor(L.data(), c->D, packed.data());
+        CK(c, cudaMalloc(&c->model_chol, packed.size() * sizeof(double)));
+        CK(c, cudaMemcpy(c->model_chol, packed.data(), packed.size() * sizeof(double),
+                         cudaMemcpyHostToDevice));
+        m.chol = c->model_chol;
+      }
+    }
+  }
+  c->model = m;
+  c->have_model = true;
+  return EB_OK;
+}
+
+// ---- log-prob ----------------------------------------------------------------
+static int ensure_scratch(eb_ctx* c, size_t rows) {
+  if (rows <= c->scratch_rows) return EB_OK;
+  CK(c, cudaStreamSynchronize(c->st));
+  cudaFree(c->scratch_x);
+  cudaFree(c->scratch_lp);
+  c->scratch_x = nullptr;
+  c->scratch_lp = nullptr;
+  c->scratch_rows = 0;
+  CK(c, cudaMalloc(&c->scratch_x, rows * (size_t)c->D * sizeof(double)));
+  CK(c, cudaMalloc(&c->scratch_lp, rows * sizeof(double)));
+  c->scratch_rows = rows;
+  return EB_OK;
+}
+
+int eb_compute_log_prob(eb_ctx* c, const double* coords, size_t m, double* out) {
+  if (!c) return EB_ERR_INVALID;
+  if (!c->have_model) FAIL(c, EB_ERR_STATE, "eb_compute_log_prob: no model set");
+  if (m == 0) return EB_OK;
+  if (!coords || !out) FAIL(c, EB_ERR_INVALID, "eb_compute_log_prob: null buffer");
+  CK(c, cudaSetDevice(c->device));
+  int rc = ensure_scratch(c, m);
+  if (rc) return rc;
+  CK(c, cudaMemcpyAsync(c->scratch_x, coords, m * (size_t)c->D * sizeof(double), cudaMemcpyHostToDevice,
+                        c->st));
+  CK(c, launch_logprob_generic(c->model, c->scratch_x, (int64_t)m, c->D, c->scratch_lp, c->status_dev, c->st));
+  CK(c, cudaMemcpyAsync(out, c->scratch_lp, m * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  return fetch_status(c);
+}
+
+// ---- state -------------------------------------------------------------------
+int eb_set_state(eb_ctx* c, const double* coords, const double* log_prob) {
+  if (!c) return EB_ERR_INVALID;
+  if (!coords) FAIL(c, EB_ERR_INVALID, "eb_set_state: coords is null");
+  if (!c->have_model) FAIL(c, EB_ERR_STATE, "eb_set_state: no model set");
+  CK(c, cudaSetDevice(c->device));
+  const size_t nd = (size_t)c->N * (size_t)c->D;
+  c->have_state = false;
+  if (log_prob) {
+    for (int64_t w = 0; w < c->N; ++w)
+      if (isnan(log_prob[w])) FAIL(c, EB_ERR_NAN_INITIAL, "The initial log_prob was NaN");  // ensemble.py:357-358
+  }
+  CK(c, cudaMemcpyAsync(c->coords, coords, nd * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  if (log_prob) {
+    CK(c, cudaMemcpyAsync(c->logp, log_prob, (size_t)c->N * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+  } else {
+    CK(c, launch_logprob_generic(c->model, c->coords, c->N, c->D, c->logp, c->status_dev, c->st));
+    int rc = fetch_status(c);
+    if (rc) return rc;
+  }
+  c->have_state = true;
+  return EB_OK;
+}
+
+int eb_get_state(eb_ctx* c, double* coords, double* log_prob) {
+  if (!c) return EB_ERR_INVALID;
+  if (!c->have_state) FAIL(c, EB_ERR_STATE, "eb_get_state: no state set");
+  CK(c, cudaSetDevice(c->device));
+  if (coords)
+    CK(c, cudaMemcpyAsync(coords, c->coords, (size_t)c->N * c->D * sizeof(double), cudaMemcpyDeviceToHost,
+                          c->st));
+  if (log_prob)
+    CK(c, cudaMemcpyAsync(log_prob, c->logp, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CK(c, cudaStreamSynchronize(c->st));
+  return EB_OK;
+}
+
+int eb_set_rng(eb_ctx* c, uint64_t seed, uint64_t step) {
+  if (!c) return EB_ERR_INVALID;
+  c->seed = seed;
+  c->step = step;
+  return EB_OK;
+}
+
+int eb_get_rng(const eb_ctx* c, uint64_t* seed, uint64_t* step) {
+  if (!c) return EB_ERR_INVALID;
+  if (seed) *seed = c->seed;
+  if (step) *step = c->step;
+  return EB_OK;
+}
+
+}  // extern "C"
+
+// ---- the hot path --------------------------------------------------------------
+namespace {
+
+struct Schedule {
+  std::vector<eb_move> moves;
+  std::vector<double> cdf;
+};
+
+int build_schedule(eb_ctx* c, const eb_move* moves, size_t nmoves, Schedule& s) {
+  if (!moves || nmoves == 0) FAIL(c, EB_ERR_INVALID, "eb_step: empty move schedule");
+  s.moves.assign(moves, moves + nmoves);
+  double tot = 0.0;
+  for (const eb_move& m : s.moves) {
+    if (m.kind < EB_MOVE_STRETCH || m.kind > EB_MOVE_SNOOKER)
+      FAIL(c, EB_ERR_INVALID, "eb_step: unknown move kind %d", m.kind);
+    if (m.nsplits < 2 || m.nsplits > MAX_SPLITS || m.nsplits > c->N)
+      FAIL(c, EB_ERR_UNSUPPORTED, "eb_step: nsplits must be in [2, min(%d, nwalkers)] (got %d)", MAX_SPLITS,
+           m.nsplits);
+    if (m.kind == EB_MOVE_SNOOKER && m.nsplits != 4)
+      FAIL(c, EB_ERR_INVALID, "eb_step: DESnookerMove uses nsplits = 4 (de_snooker.py:28)");
+    if (m.kind == EB_MOVE_DE && c->N - (c->N + m.nsplits - 1) / m.nsplits < 2)
+      FAIL(c, EB_ERR_INVALID, "eb_step: DEMove needs at least 2 complement walkers");
+    if (!(m.weight >= 0.0) || !isfinite(m.weight)) FAIL(c, EB_ERR_INVALID, "eb_step: bad move weight");
+    if (m.kind == EB_MOVE_STRETCH && !(m.p0 > 0.0)) FAIL(c, EB_ERR_INVALID, "eb_step: stretch scale a must be > 0");
+    tot += m.weight;
+  }
+  if (!(tot > 0.0)) FAIL(c, EB_ERR_INVALID, "eb_step: move weights sum to zero");
+  // ensemble.py:128-129 then RandomState.choice(p=...): cdf = cumsum(p); cdf /= cdf[-1]
+  s.cdf.resize(nmoves);
+  double run = 0.0;
+  for (size_t k = 0; k < nmoves; ++k) {
+    run += s.moves[k].weight / tot;
+    s.cdf[k] = run;
+  }
+  for (size_t k = 0; k < nmoves; ++k) s.cdf[k] /= run;
+  return EB_OK;
+}
+
+// ensemble.py:406 -- one move per step for the whole ensemble
+size_t choose_move(const eb_ctx* c, const Schedule& s, uint64_t step) {
+  if (s.moves.size() == 1) return 0;
+  const u32x4 w = draw_words(c->seed, step, 0, TAG_MOVE, 0);
+  const double u = u53(w.x, w.y);
+  size_t idx = 0;
+  while (idx + 1 < s.cdf.size() && !(s.cdf[idx] > u)) ++idx;  // searchsorted(side="right")
+  return idx;
+}
+
+// launch the P half-steps of one step
+int launch_step(eb_ctx* c, const eb_move& mv, uint64_t step, const int32_t* order, uint64_t& launches) {
+  const int P = mv.nsplits;
+  const int64_t N = c->N;
+  if (N < 2 * (int64_t)c->D && !mv.live_dangerously)  // red_blue.py:64-70
+    FAIL(c, EB_ERR_FEW_WALKERS,
+         "It is unadvisable to use a red-blue move with fewer walkers than twice the number of dimensions.");
+  int start[MAX_SPLITS + 1];
+  start[0] = 0;
+  for (int j = 0; j < P; ++j) start[j + 1] = start[j] + (int)((N - j + P - 1) / P);
+
+  HalfStepArgs a{};
+  a.coords = c->coords;
+  a.logp = c->logp;
+  a.accepted = c->accepted;
+  a.nacc = c->nacc;
+  a.status = c->status_dev;
+  a.order = order;
+  a.N = N;
+  a.D = c->D;
+  a.seed = c->seed;
+  a.step = step;
+  a.model = c->model;
+  if (c->debug) {
+    a.tap_partners = c->tap_partners;
+    a.tap_scalar = c->tap_scalar;
+    a.tap_u = c->tap_u;
+    a.tap_active = c->tap_active;
+  }
+  switch (mv.kind) {
+    case EB_MOVE_STRETCH:
+      a.p0 = mv.p0;
+      break;
+    case EB_MOVE_DE:
+      a.p0 = isnan(mv.p1) ? 2.38 / sqrt(2.0 * (double)c->D) : mv.p1;  // de.py:33-38
+      a.p1 = mv.p0;                                                    // sigma
+      break;
+    default:
+      a.p0 = mv.p0;  // gammas
+  }
+  comm_fill_args(c->comm, a);
+  const bool dmma = c->allow_dmma && mv.kind == EB_MOVE_STRETCH && c->model.kind == EB_MODEL_GAUSS_DENSE &&
+                    c->model.chol != nullptr && !c->debug;
+  for (int split = 0; split < P; ++split) {
+    a.split = split;
+    a.a_start = start[split];
+    a.a_count = start[split + 1] - start[split];
+    int k = 0;
+    for (int j = 0; j < P && k < 3; ++j) {
+      if (j == split) continue;
+      a.c_start[k] = start[j];
+      a.c_count[k] = start[j + 1] - start[j];
+      ++k;
+    }
+    int rc = comm_active_range(c->comm, c->st, a, order);  // i_lo / i_hi for this rank
+    if (rc) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+    if (dmma) {
+      CK(c, launch_half_step_dense_dmma(a, c->sm_count, c->st));
+      c->last_kernel = "dense_dmma";
+    } else {
+      CK(c, launch_half_step_generic(mv.kind, a, c->st));
+      c->last_kernel = "generic";
+    }
+    ++launches;
+    c->tap_count = a.a_count;
+    rc = comm_after_split(c->comm, c->st, a, launches);  // exchange the updated rows
+    if (rc) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+  }
+  return EB_OK;
+}
+
+// run nsteps steps; `after_step(k)` is called (with work for step k enqueued)
+// when non-null and may enqueue copies on the stream
+template <class F>
+int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, F&& after_step) {
+  uint64_t launches = 0;
+  const bool perstep = c->l2_flush;  // flush L2 before every step, time each step on its own
+  if (perstep) {
+    if (nsteps > 16384) FAIL(c, EB_ERR_INVALID, "l2_flush mode times each step separately; use nsteps <= 16384");
+    if (!c->flush_buf) CK(c, cudaMalloc(&c->flush_buf, c->flush_bytes));
+    while (c->ev_pool.size() < 2 * nsteps) {
+      cudaEvent_t e;
+      CK(c, cudaEventCreate(&e));
+      c->ev_pool.push_back(e);
+    }
+  }
+  CK(c, cudaEventRecord(c->ev0, c->st));
+  std::vector<size_t> pick;
+  uint64_t done = 0;
+  while (done < nsteps) {
+    const size_t chunk = (size_t)std::min<uint64_t>(nsteps - done, c->table_cap);
+    pick.resize(chunk);
+    CK(c, cudaStreamSynchronize(c->st));  // info_host is reused per chunk
+    for (size_t k = 0; k < chunk; ++k) {
+      pick[k] = choose_move(c, s, c->step + k);
+      c->info_host[k].nsplits = s.moves[pick[k]].nsplits;
+      c->info_host[k].randomize = s.moves[pick[k]].randomize_split;
+    }
+    for (size_t k = 0; k < chunk; ++k) {
+      if (perstep) {
+        CK(c, cudaMemsetAsync(c->flush_buf, (int)(k & 0xff), c->flush_bytes, c->st));
+        CK(c, cudaEventRecord(c->ev_pool[2 * (done + k)], c->st));
+      }
+      if (k == 0) {
+        // split tables of the whole chunk (charged to the chunk's first step)
+        CK(c, cudaMemcpyAsync(c->info_dev, c->info_host, chunk * sizeof(StepInfo), cudaMemcpyHostToDevice, c->st));
+        CK(c, launch_split_tables(c->order, c->info_dev, (int)chunk, c->N, c->seed, c->step, c->st));
+        ++launches;
+      }
+      int rc = launch_step(c, s.moves[pick[k]], c->step, c->order + k * (size_t)c->N, launches);
+      if (rc) return rc;
+      c->step += 1;
+      if (perstep) CK(c, cudaEventRecord(c->ev_pool[2 * (done + k) + 1], c->st));
+      rc = after_step(done + k);
+      if (rc) return rc;
+    }
+    done += chunk;
+  }
+  CK(c, cudaEventRecord(c->ev1, c->st));
+  CK(c, cudaMemcpyAsync(c->status_host, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  CK(c, cudaStreamSynchronize(c->st));
+  float ms = 0.f;
+  if (perstep) {
+    double tot = 0.0;
+    for (uint64_t k = 0; k < nsteps; ++k) {
+      CK(c, cudaEventElapsedTime(&ms, c->ev_pool[2 * k], c->ev_pool[2 * k + 1]));
+      tot += ms;
+    }
+    c->last_ms = tot;
+  } else {
+    CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_ms = ms;
+  }
+  c->last_launches = launches;
+  return check_status(c);
+}
+
+int step_preflight(eb_ctx* c) {
+  if (!c->have_model) FAIL(c, EB_ERR_STATE, "eb_step: no model set");
+  if (!c->have_state) FAIL(c, EB_ERR_STATE, "eb_step: no state set");
+  CK(c, cudaSetDevice(c->device));
+  return EB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eb_step(eb_ctx* c, const eb_move* moves, size_t nmoves, uint64_t nsteps, uint8_t* accepted_last) {
+  if (!c) return EB_ERR_INVALID;
+  int rc = step_preflight(c);
+  if (rc) return rc;
+  Schedule s;
+  rc = build_schedule(c, moves, nmoves, s);
+  if (rc) return rc;
+  if (nsteps > 0) {
+    rc = run_steps(c, s, nsteps, [](uint64_t) { return EB_OK; });
+    if (rc) return rc;
+  }
+  if (accepted_last) {
+    CK(c, cudaMemcpyAsync(accepted_last, c->accepted, (size_t)c->N, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+  }
+  return EB_OK;
+}
+
+int eb_step_store(eb_ctx* c, const eb_move* moves, size_t nmoves, uint64_t nsteps, uint64_t thin_by,
+                  double* chain, double* log_prob, double* accepted) {
+  if (!c) return EB_ERR_INVALID;
+  if (thin_by == 0) FAIL(c, EB_ERR_INVALID, "Invalid thinning argument");  // ensemble.py:380-381
+  if (!chain || !log_prob) FAIL(c, EB_ERR_INVALID, "eb_step_store: null output buffer");
+  int rc = step_preflight(c);
+  if (rc) return rc;
+  Schedule s;
+  rc = build_schedule(c, moves, nmoves, s);
+  if (rc) return rc;
+  const size_t N = (size_t)c->N, D = (size_t)c->D;
+  const size_t row = N * D + N;  // coords then log_prob, staged together
+  for (int k = 0; k < 2; ++k) {
+    if (!c->stage[k]) {
+      CK(c, cudaMallocHost(&c->stage[k], row * sizeof(double)));
+      CK(c, cudaMallocHost(&c->stage_acc[k], N));
+      CK(c, cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming));
+    }
+  }
+  // double-buffered pinned staging: the D2H of stored step k overlaps the
+  // kernels of the following steps; the host drains slot k-1 while k is in flight
+  uint64_t stored = 0;
+  int64_t pending[2] = {-1, -1};
+  auto drain = [&](int slot) -> int {
+    if (pending[slot] < 0) return EB_OK;
+    CK(c, cudaEventSynchronize(c->stage_ev[slot]));
+    const size_t k = (size_t)pending[slot];
+    memcpy(chain + k * N * D, c->stage[slot], N * D * sizeof(double));          // backend.py:224
+    memcpy(log_prob + k * N, c->stage[slot] + N * D, N * sizeof(double));        // backend.py:225
+    if (accepted)
+      for (size_t w = 0; w < N; ++w) accepted[w] += (double)c->stage_acc[slot][w];  // backend.py:229
+    pending[slot] = -1;
+    return EB_OK;
+  };
+  rc = run_steps(c, s, nsteps, [&](uint64_t k) -> int {
+    if ((k + 1) % thin_by != 0) return EB_OK;  // ensemble.py:416
+    const int slot = (int)(stored & 1);
+    int r = drain(slot);
+    if (r) return r;
+    CK(c, cudaMemcpyAsync(c->stage[slot], c->coords, N * D * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaMemcpyAsync(c->stage[slot] + N * D, c->logp, N * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaMemcpyAsync(c->stage_acc[slot], c->accepted, N, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaEventRecord(c->stage_ev[slot], c->st));
+    pending[slot] = (int64_t)stored;
+    ++stored;
+    return EB_OK;
+  });
+  int r0 = drain((int)(stored & 1));
+  int r1 = drain((int)((stored + 1) & 1));
+  if (rc) return rc;
+  if (r0) return r0;
+  return r1;
+}
+
+int eb_get_naccepted(eb_ctx* c, uint64_t* naccepted) {
+  if (!c || !naccepted) return EB_ERR_INVALID;
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaMemcpyAsync(naccepted, c->nacc, (size_t)c->N * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->st));
+  CK(c, cudaStreamSynchronize(c->st));
+  return EB_OK;
+}
+
+int eb_reset_counters(eb_ctx* c) {
+  if (!c) return EB_ERR_INVALID;
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaMemsetAsync(c->nacc, 0, (size_t)c->N * sizeof(unsigned long long), c->st));
+  CK(c, cudaStreamSynchronize(c->st));
+  return EB_OK;
+}
+
+int eb_last_step_timing(const eb_ctx* c, double* ms, uint64_t* launches) {
+  if (!c) return EB_ERR_INVALID;
+  if (ms) *ms = c->last_ms;
+  if (launches) *launches = c->last_launches;
+  return EB_OK;
+}
+
+const char* eb_last_kernel_name(const eb_ctx* c) { return c ? c->last_kernel : "none"; }
+
+int eb_set_option(eb_ctx* c, const char* name, int64_t value) {
+  if (!c || !name) return EB_ERR_INVALID;
+  if (!strcmp(name, "debug_taps")) {
+    CK(c, cudaSetDevice(c->device));
+    if (value && !c->tap_scalar) {
+      const size_t N = (size_t)c->N;
+      CK(c, cudaMalloc(&c->tap_partners, 3 * N * sizeof(int64_t)));
+      CK(c, cudaMalloc(&c->tap_scalar, N * sizeof(double)));
+      CK(c, cudaMalloc(&c->tap_u, N * sizeof(double)));
+      CK(c, cudaMalloc(&c->tap_active, N * sizeof(int64_t)));
+    }
+    c->debug = value != 0;
+    return EB_OK;
+  }
+  if (!strcmp(name, "l2_flush")) {
+    c->l2_flush = value != 0;
+    return EB_OK;
+  }
+  if (!strcmp(name, "dense_dmma")) {
+    c->allow_dmma = value != 0;
+    return EB_OK;
+  }
+  FAIL(c, EB_ERR_INVALID, "eb_set_option: unknown option '%s'", name);
+}
+
+int eb_debug_taps(eb_ctx* c, int64_t* partners, double* scalar, double* u_accept, int64_t* active,
+                  int64_t* nactive) {
+  if (!c) return EB_ERR_INVALID;
+  if (!c->debug || !c->tap_scalar) FAIL(c, EB_ERR_STATE, "eb_debug_taps: enable with eb_set_option(\"debug_taps\", 1)");
+  CK(c, cudaSetDevice(c->device));
+  const size_t N = (size_t)c->N;
+  if (partners) CK(c, cudaMemcpy(partners, c->tap_partners, 3 * N * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (scalar) CK(c, cudaMemcpy(scalar, c->tap_scalar, N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (u_accept) CK(c, cudaMemcpy(u_accept, c->tap_u, N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (active) CK(c, cudaMemcpy(active, c->tap_active, N * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (nactive) *nactive = c->tap_count;
+  return EB_OK;
+}
+
+int eb_host_alloc(size_t bytes, void** out) {
+  if (!out || bytes == 0) return EB_ERR_INVALID;
+  if (cudaMallocHost(out, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    *out = nullptr;
+    return EB_ERR_CUDA;
+  }
+  return EB_OK;
+}
+
+int eb_host_free(void* ptr) {
+  if (ptr && cudaFreeHost(ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return EB_ERR_CUDA;
+  }
+  return EB_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------
+int eb_comm_id(char id[EB_COMM_ID_BYTES]) { return comm_unique_id(id) ? EB_ERR_COMM : EB_OK; }
+
+int eb_comm_init(eb_ctx* c, const char id[EB_COMM_ID_BYTES], int rank, int nranks, int mode) {
+  if (!c) return EB_ERR_INVALID;
+  CK(c, cudaSetDevice(c->device));
+  if (comm_init(c->comm, id, rank, nranks, mode, c->N, c->D, c->coords, c->st)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+  return EB_OK;
+}
+
+int eb_comm_export(eb_ctx* c, char blob[EB_IPC_BLOB_BYTES]) {
+  if (!c) return EB_ERR_INVALID;
+  CK(c, cudaSetDevice(c->device));
+  if (comm_export(c->comm, blob)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+  return EB_OK;
+}
+
+int eb_comm_import(eb_ctx* c, const char* blobs) {
+  if (!c) return EB_ERR_INVALID;
+  CK(c, cudaSetDevice(c->device));
+  if (comm_import(c->comm, blobs)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+  return EB_OK;
+}
+
+}  // extern "C"

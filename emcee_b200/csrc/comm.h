@@ -1,0 +1,54 @@
+// Multi-GPU plumbing of the engine: one process per GPU, walkers sharded by
+// contiguous row block (rank r owns walkers [r*N/R, (r+1)*N/R)).
+//   EB_COMM_ALLGATHER: every rank keeps a full replica of coords; after each
+//     split one in-place ncclAllGather of the owned row blocks (NCCL is
+//     dlopen-ed, so single-GPU use needs no NCCL at all).
+//   EB_COMM_P2P: no replica traffic; the half-step kernel loads partner rows
+//     straight from the owner's HBM over NVLink (cudaIpc-mapped peer pointers)
+//     and ranks meet at a flag barrier in peer memory between splits.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "engine.cuh"
+
+namespace eb {
+
+constexpr int MAX_RANKS = 16;
+
+struct Comm {
+  int rank = 0, nranks = 1, mode = EB_COMM_ALLGATHER;
+  int64_t N = 0;
+  int D = 0;
+  int64_t rows_per_rank = 0;
+  double* coords = nullptr;  // this rank's [N, D] buffer
+  // NCCL (dlopen)
+  void* lib = nullptr;
+  void* nccl = nullptr;
+  // P2P
+  void* peer_base[MAX_RANKS] = {nullptr};
+  const double** peer_coords_dev = nullptr;   // device array [nranks]
+  unsigned* flags = nullptr;                  // this rank's barrier flags [MAX_RANKS] (device, exported)
+  unsigned* peer_flags[MAX_RANKS] = {nullptr};
+  unsigned** peer_flags_dev = nullptr;
+  unsigned epoch = 0;
+  bool imported = false;
+  std::string err;
+};
+
+int comm_unique_id(char* id128);
+int comm_init(Comm& c, const char* id128, int rank, int nranks, int mode, int64_t N, int D, double* coords,
+              cudaStream_t st);
+int comm_export(Comm& c, char* blob);
+int comm_import(Comm& c, const char* blobs);
+void comm_destroy(Comm& c);
+// peer pointers / ownership for the kernels
+void comm_fill_args(const Comm& c, HalfStepArgs& a);
+// [i_lo, i_hi): the active ranks of this split owned by this rank
+int comm_active_range(Comm& c, cudaStream_t st, HalfStepArgs& a, const int32_t* order);
+// make the rows updated in this split visible to every rank
+int comm_after_split(Comm& c, cudaStream_t st, const HalfStepArgs& a, uint64_t& launches);
+
+}  // namespace eb

@@ -1,0 +1,84 @@
+// Internal types shared by the kernels and the C ABI (not part of the boundary).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/emcee_b200.h"
+#include "philox.cuh"
+
+namespace eb {
+
+constexpr int MAX_SPLITS = 32;      // split_table_kernel uses one warp per set
+constexpr int TABLE_THREADS = 1024;
+
+// device status flags (OR-ed by kernels, read back after every call)
+enum : int {
+  FLAG_NAN_LOGPROB = 1,
+  FLAG_INF_PARAM = 2,
+  FLAG_NAN_PARAM = 4,
+};
+
+struct ModelDev {
+  int kind;
+  const double* params;  // device: gauss_dense mu[D], A[D*D]; else unused
+  const double* chol;    // device: gauss_dense packed factor for the DMMA kernel (or null)
+  double s0, s1;         // rosenbrock a,b ; ring R,sigma
+};
+
+// per-step split description handed to split_table_kernel
+struct StepInfo {
+  int32_t nsplits;
+  int32_t randomize;
+};
+
+// everything one half-step (one split of one step) needs
+struct HalfStepArgs {
+  double* coords;            // [N, D] row-major, live state
+  double* logp;              // [N]
+  uint8_t* accepted;         // [N] accept mask of the current step
+  unsigned long long* nacc;  // [N] accepted-proposal counters
+  int* status;               // flags
+  const int32_t* order;      // [N] walker ids grouped by set, ascending inside a set
+  const double* const* peer_coords;  // P2P mode: [nranks] peer-mapped coords (or null)
+  int64_t rows_per_rank;     // P2P mode: owner(w) = w / rows_per_rank
+  int64_t N;
+  int D;
+  int split;
+  int a_start, a_count;  // active set = order[a_start .. a_start + a_count)
+  int i_lo, i_hi;        // active ranks processed by this GPU
+  int c_start[3], c_count[3];  // snooker: the three complement sets (ascending j != split)
+  uint64_t seed, step;
+  double p0, p1;  // stretch: a | de: g0, sigma | snooker: gammas
+  ModelDev model;
+  // optional taps (null unless debugging is enabled)
+  int64_t* tap_partners;  // [3, N]
+  double* tap_scalar;     // [N]
+  double* tap_u;          // [N]
+  int64_t* tap_active;    // [N]
+};
+
+struct Engine;  // defined in capi.cu
+
+// ---- kernel launchers (implemented in the .cu files) ----------------------
+cudaError_t launch_split_tables(int32_t* order, const StepInfo* info_dev, int nsteps_chunk, int64_t N,
+                                uint64_t seed, uint64_t step0, cudaStream_t st);
+cudaError_t launch_half_step_generic(int move_kind, const HalfStepArgs& a, cudaStream_t st);
+cudaError_t launch_logprob_generic(const ModelDev& m, const double* x, int64_t rows, int D, double* out,
+                                   int* status, cudaStream_t st);
+// specialised: stretch + dense Gaussian on FP64 tensor cores (DMMA).  Returns
+// cudaErrorNotSupported when the shape is outside its envelope.
+bool dense_dmma_supported(int D);
+size_t dense_dmma_factor_doubles(int D);
+void dense_dmma_pack_factor(const double* L, int D, double* packed);  // host
+cudaError_t launch_half_step_dense_dmma(const HalfStepArgs& a, int sm_count, cudaStream_t st);
+
+inline int lanes_per_walker(int D) {
+  int g = 4;
+  while (g < 32 && g * 4 < D) g <<= 1;
+  return g;
+}
+
+}  // namespace eb

@@ -1,0 +1,313 @@
+"""``EnsembleSampler`` on the B200 engine (reference:
+``src/emcee/ensemble.py:32-623``).
+
+Same constructor / ``sample`` / ``run_mcmc`` / ``compute_log_prob`` surface and
+the same exceptions, but ``log_prob_fn`` is a registered device model
+(``emcee_b200.models``) and every step runs inside the CUDA library through the
+C ABI: the walker array stays in HBM between steps, ``run_mcmc`` is one call
+for all iterations, and stored steps stream back through pinned buffers.
+Features that need a host callback per walker (``pool``, ``args``/``kwargs``,
+blobs, named parameters) raise ``NotImplementedError``."""
+
+from collections.abc import Iterable
+
+import numpy as np
+
+from . import _lib
+from .backend import Backend
+from .model import Model
+from .models import DeviceModel
+from .moves import StretchMove
+from .rng import DeviceRandom
+from .state import State
+
+__all__ = ["EnsembleSampler", "walkers_independent"]
+
+
+def _seed_from_numpy():
+    """Like the reference, start from numpy's global generator
+    (``ensemble.py:140`` ``state = np.random.get_state()``) without consuming it."""
+    keys, pos = np.random.get_state()[1:3]
+    a, b = int(keys[pos % 624]), int(keys[(pos + 1) % 624])
+    return ((a << 32) | b) ^ (int(pos) * 0x9E3779B97F4A7C15 & (2**64 - 1))
+
+
+class EnsembleSampler(object):
+    """An ensemble MCMC sampler whose walker update runs on one B200.
+
+    Args mirror ``ensemble.py:79-98``.  Extra keyword-only arguments: ``seed``
+    (Philox key; default derived from numpy's global state) and ``device``."""
+
+    def __init__(
+        self,
+        nwalkers,
+        ndim,
+        log_prob_fn,
+        pool=None,
+        moves=None,
+        args=None,
+        kwargs=None,
+        backend=None,
+        vectorize=False,
+        blobs_dtype=None,
+        parameter_names=None,
+        # deprecated in the reference; rejected here
+        a=None,
+        postargs=None,
+        threads=None,
+        live_dangerously=None,
+        runtime_sortingfn=None,
+        *,
+        seed=None,
+        device=0,
+    ):
+        for name, val in (("a", a), ("postargs", postargs), ("threads", threads),
+                          ("live_dangerously", live_dangerously), ("runtime_sortingfn", runtime_sortingfn)):
+            if val is not None:
+                raise NotImplementedError("the deprecated '%s' argument is not supported; use 'moves'" % name)
+        if not isinstance(log_prob_fn, DeviceModel):
+            raise TypeError(
+                "log_prob_fn must be a registered device model (emcee_b200.models.*): the "
+                "walker update runs on the GPU and cannot call back into Python"
+            )
+        if pool is not None:
+            raise NotImplementedError("pool: log-probabilities are evaluated on the GPU, not through map()")
+        if args or kwargs:
+            raise NotImplementedError("args/kwargs: put the parameters into the device model")
+        if parameter_names is not None:
+            raise NotImplementedError("parameter_names need a host callable")
+        if blobs_dtype is not None:
+            raise NotImplementedError("blobs are not supported on the device path")
+
+        # move schedule (ensemble.py:115-129)
+        if moves is None:
+            self._moves, weights = [StretchMove()], [1.0]
+        elif isinstance(moves, Iterable):
+            moves = list(moves)
+            try:
+                self._moves, weights = (list(t) for t in zip(*moves))
+            except TypeError:
+                self._moves, weights = moves, np.ones(len(moves))
+        else:
+            self._moves, weights = [moves], [1.0]
+        self._raw_weights = np.atleast_1d(weights).astype(float)
+        self._weights = self._raw_weights / np.sum(self._raw_weights)
+
+        self.pool = None
+        self.vectorize = True  # the device path is always batched
+        self.blobs_dtype = None
+        self.ndim = int(ndim)
+        self.nwalkers = int(nwalkers)
+        self.log_prob_fn = log_prob_fn
+        self.params_are_named = False
+
+        self._engine = _lib.Engine(self.nwalkers, self.ndim, _seed_from_numpy() if seed is None else seed,
+                                   device=device)
+        self._engine.set_model(log_prob_fn.kind, log_prob_fn.device_params(self.ndim))
+        self._random = DeviceRandom(self._engine)
+
+        self.backend = Backend() if backend is None else backend
+        if not self.backend.initialized:  # ensemble.py:137-141
+            self._previous_state = None
+            self.reset()
+        else:
+            if self.backend.shape != (self.nwalkers, self.ndim):
+                raise ValueError(
+                    "the shape of the backend ({0}) is incompatible with the "
+                    "shape of the sampler ({1})".format(self.backend.shape, (self.nwalkers, self.ndim))
+                )
+            self.random_state = self.backend.random_state  # silently ignored if foreign
+            if self.backend.iteration > 0:
+                self._previous_state = self.get_last_sample()
+            else:
+                self._previous_state = None
+
+    # ------------------------------------------------------------------ state
+    @property
+    def random_state(self):
+        """``("philox4x32-10", seed, step)`` -- the complete random state."""
+        return self._random.get_state()
+
+    @random_state.setter
+    def random_state(self, state):
+        # like ensemble.py:228-238: try, and stay as we are if it is garbage
+        try:
+            self._random.set_state(state)
+        except Exception:
+            pass
+
+    @property
+    def iteration(self):
+        return self.backend.iteration
+
+    def reset(self):
+        self.backend.reset(self.nwalkers, self.ndim)
+
+    def __getstate__(self):
+        raise NotImplementedError("a sampler that owns GPU memory cannot be pickled")
+
+    # ------------------------------------------------------------- the driver
+    def _schedule(self):
+        return [(m.descriptor(), w) for m, w in zip(self._moves, self._raw_weights)]
+
+    def sample(
+        self,
+        initial_state,
+        log_prob0=None,
+        rstate0=None,
+        blobs0=None,
+        iterations=1,
+        tune=False,
+        skip_initial_state_check=False,
+        thin_by=1,
+        thin=None,
+        store=True,
+        progress=False,
+        progress_kwargs=None,
+        _bulk=False,
+    ):
+        """Advance the chain as a generator (``ensemble.py:258-424``): yields the
+        live :class:`State` every ``thin_by`` steps."""
+        if log_prob0 is not None or rstate0 is not None or blobs0 is not None:
+            raise NotImplementedError("log_prob0/rstate0/blobs0 are deprecated in the reference; pass a State")
+        if progress:
+            raise NotImplementedError("progress bars are outside the hot path")
+        if iterations is None and store:
+            raise ValueError("'store' must be False when 'iterations' is None")
+
+        state = State(initial_state, copy=True)  # the caller's arrays are never touched
+        state_shape = np.shape(state.coords)
+        if state_shape != (self.nwalkers, self.ndim):
+            raise ValueError("incompatible input dimensions {0}".format(state_shape))
+        if state.blobs is not None:
+            raise NotImplementedError("blobs are not supported on the device path")
+        if (not skip_initial_state_check) and (not walkers_independent(state.coords)):
+            raise ValueError(
+                "Initial state has a large condition number. "
+                "Make sure that your walkers are linearly independent for the "
+                "best performance"
+            )
+        self.random_state = state.random_state  # ensemble.py:335 (ignored if None/foreign)
+
+        if state.log_prob is not None and np.shape(state.log_prob) != (self.nwalkers,):
+            raise ValueError("incompatible input dimensions")
+        # upload; a missing log_prob is evaluated on the device (ensemble.py:350-358)
+        self._engine.set_state(state.coords, state.log_prob)
+
+        if thin is not None:  # deprecated form: store every `thin`-th, yield every step
+            thin = int(thin)
+            if thin <= 0:
+                raise ValueError("Invalid thinning argument")
+            yield_step, checkpoint_step = 1, thin
+            if store:
+                self.backend.grow(iterations // checkpoint_step, None)
+        else:
+            thin_by = int(thin_by)
+            if thin_by <= 0:
+                raise ValueError("Invalid thinning argument")
+            yield_step = checkpoint_step = thin_by
+            if store:
+                self.backend.grow(iterations, None)
+
+        native_store = store and type(self.backend) is Backend
+        sched = self._schedule()
+        eng = self._engine
+
+        def refresh():
+            state.coords, state.log_prob = eng.get_state()
+            state.random_state = self.random_state
+
+        if _bulk and iterations is not None and (not store or (native_store and thin is None)):
+            # run_mcmc: the whole run is one C-ABI call
+            total = iterations * yield_step
+            if total > 0:
+                if store:
+                    b = self.backend
+                    k0, k1 = b.iteration, b.iteration + iterations
+                    eng.step_store(sched, total, checkpoint_step, b.chain[k0:k1], b.log_prob[k0:k1], b.accepted)
+                    b.iteration = k1
+                    b.random_state = self.random_state
+                else:
+                    eng.step(sched, total, want_accepted=False)
+            refresh()
+            if iterations > 0:
+                yield state
+            return
+
+        i = 0
+        counter = iter(int, 1) if iterations is None else range(iterations)
+        for _ in counter:
+            # the steps of this yield window; at most the last one is stored
+            last_is_checkpoint = store and (i + yield_step) % checkpoint_step == 0
+            if last_is_checkpoint and native_store:
+                b = self.backend
+                k = b.iteration
+                eng.step_store(sched, yield_step, yield_step, b.chain[k : k + 1], b.log_prob[k : k + 1], b.accepted)
+                b.iteration = k + 1
+                b.random_state = self.random_state
+                refresh()
+            else:
+                accepted = eng.step(sched, yield_step, want_accepted=last_is_checkpoint)
+                refresh()
+                if last_is_checkpoint:
+                    self.backend.save_step(state, accepted)
+            i += yield_step
+            yield state
+
+    def run_mcmc(self, initial_state, nsteps, **kwargs):
+        """Iterate :func:`sample` for ``nsteps`` iterations and return the last
+        state (``ensemble.py:426-456``); ``initial_state=None`` resumes."""
+        if initial_state is None:
+            if self._previous_state is None:
+                raise ValueError("Cannot have `initial_state=None` if run_mcmc has never been called.")
+            initial_state = self._previous_state
+        results = None
+        for results in self.sample(initial_state, iterations=nsteps, _bulk=True, **kwargs):
+            pass
+        self._previous_state = results
+        return results
+
+    def compute_log_prob(self, coords):
+        """``(log_prob, None)`` for ``coords[..., ndim]`` evaluated on the device
+        (``ensemble.py:458-553``); raises ``ValueError`` for non-finite
+        parameters or a NaN log-probability like the reference."""
+        return self._engine.compute_log_prob(np.asarray(coords, dtype=np.float64)), None
+
+    # ---------------------------------------------------------------- results
+    @property
+    def acceptance_fraction(self):
+        return self.backend.accepted / float(self.backend.iteration)
+
+    def get_chain(self, **kwargs):
+        return self.get_value("chain", **kwargs)
+
+    def get_blobs(self, **kwargs):
+        return self.get_value("blobs", **kwargs)
+
+    def get_log_prob(self, **kwargs):
+        return self.get_value("log_prob", **kwargs)
+
+    def get_last_sample(self, **kwargs):
+        return self.backend.get_last_sample()
+
+    def get_value(self, name, **kwargs):
+        return self.backend.get_value(name, **kwargs)
+
+    def get_autocorr_time(self, **kwargs):
+        return self.backend.get_autocorr_time(**kwargs)
+
+
+def walkers_independent(coords):
+    """Initial-state sanity check (``ensemble.py:653-663``): the centred,
+    column-normalised walker matrix must have condition number <= 1e8.  Runs
+    once per ``sample`` call on the host."""
+    coords = np.asarray(coords, dtype=np.float64)
+    if not np.all(np.isfinite(coords)):
+        return False
+    centred = coords - np.mean(coords, axis=0)[None, :]
+    span = np.amax(np.abs(centred), axis=0)
+    if np.any(span == 0):
+        return False
+    centred /= span
+    centred /= np.sqrt(np.sum(centred**2, axis=0))
+    return np.linalg.cond(centred) <= 1e8

@@ -96,11 +96,9 @@ def make_config(name, nwalkers=None, ndim=None, dof=None):
     """(target, p0) of one BASELINE.json config, optionally rescaled.
 
     name: "gauss_iso" | "gauss_dense" | "rosenbrock" | "ring".
-    ``dof`` for gauss_dense defaults to ``ndim`` (a Wishart with 2*ndim degrees
-    of freedom): the paper's ``dof=1`` gives condition numbers ~1e6 at D=128,
-    where the stretch move needs >1e5 steps to decorrelate and every fp64
-    summation order of the quadratic form differs in the 10th digit; ``dof=ndim``
-    keeps the target *dense and correlated* (cond ~ 30) with well-scaled fp64.
+    gauss_dense uses the paper's ``random_cov(ndim, dof=1)``: at
+    D = 128 the covariance has condition number ~3e4, so different fp64
+    summation orders of the quadratic form agree to ~1e-12 relative.
     """
     defaults = {
         "gauss_iso": (32, 5),
@@ -116,7 +114,7 @@ def make_config(name, nwalkers=None, ndim=None, dof=None):
     if name == "gauss_iso":
         return GaussIso(d), rng_p.standard_normal((n, d))
     if name == "gauss_dense":
-        cov = random_cov(d, dof=d if dof is None else dof, rng=rng_m)
+        cov = random_cov(d, dof=1 if dof is None else dof, rng=rng_m)
         icov = np.linalg.inv(cov)
         icov = 0.5 * (icov + icov.T)
         return GaussDense(icov), rng_p.standard_normal((n, d))

@@ -1,0 +1,158 @@
+"""API / error contracts of the reference's unit tests, on the device path
+(``tests/unit/test_sampler.py``, ``test_stretch.py``, ``test_state.py``)."""
+import numpy as np
+import pytest
+
+import emcee_b200
+from emcee_b200 import models, moves
+
+pytestmark = pytest.mark.gpu
+
+
+def make(nwalkers=32, ndim=3, mv=None, seed=1234):
+    return emcee_b200.EnsembleSampler(nwalkers, ndim, models.GaussianIso(), moves=mv, seed=seed)
+
+
+def test_shapes_and_move_schedules():
+    # tests/unit/test_sampler.py:32-84
+    for mv in [None, moves.DEMove(), [(moves.DEMove(), 0.8), (moves.DESnookerMove(), 0.2)],
+               [moves.StretchMove(), moves.DEMove()]]:
+        s = make(mv=mv)
+        p0 = np.random.default_rng(1).standard_normal((32, 3))
+        s.run_mcmc(p0, 20)
+        assert s.get_chain().shape == (20, 32, 3)
+        assert s.get_log_prob().shape == (20, 32)
+        assert s.get_chain(flat=True).shape == (640, 3)
+        assert s.get_chain(thin=2, discard=4).shape == (8, 32, 3)
+        assert s.acceptance_fraction.shape == (32,)
+        assert s.iteration == 20
+        last = s.get_last_sample()
+        assert np.array_equal(last.coords, s.get_chain()[-1])
+
+
+def test_errors():
+    # tests/unit/test_sampler.py:87-124
+    s = make()
+    with pytest.raises(ValueError):
+        s.run_mcmc(np.zeros((32, 4)), 1)  # wrong ndim
+    with pytest.raises(ValueError):
+        s.run_mcmc(np.zeros((32, 3)), 1)  # dependent walkers
+    with pytest.raises(ValueError):
+        s.run_mcmc(None, 1)  # never run
+    p0 = np.random.default_rng(2).standard_normal((32, 3))
+    with pytest.raises(ValueError):
+        next(s.sample(p0, iterations=None, store=True))
+    with pytest.raises(ValueError):
+        s.run_mcmc(p0, 4, thin_by=0)
+    bad = p0.copy()
+    bad[3, 1] = np.inf
+    with pytest.raises(ValueError, match="infinite"):
+        s.compute_log_prob(bad)
+    bad[3, 1] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        s.compute_log_prob(bad)
+    with pytest.raises(ValueError, match="initial log_prob"):
+        st = emcee_b200.State(p0, log_prob=np.full(32, np.nan))
+        s.run_mcmc(st, 1, skip_initial_state_check=True)
+
+
+def test_live_dangerously_guard():
+    # tests/unit/test_stretch.py:15-34 -- drives Move.propose through the Model boundary
+    nwalkers, ndim = 4, 3
+    s = emcee_b200.EnsembleSampler(nwalkers, ndim, models.GaussianIso(), seed=1)
+    coords = np.random.default_rng(3).standard_normal((nwalkers, ndim))
+    model = emcee_b200.Model(s.log_prob_fn, s.compute_log_prob, map, s._random)
+    state = emcee_b200.State(coords, log_prob=s.compute_log_prob(coords)[0])
+    with pytest.raises(RuntimeError):
+        moves.StretchMove().propose(model, state)
+    new_state, accepted = moves.StretchMove(live_dangerously=True).propose(model, state)
+    assert accepted.shape == (nwalkers,) and new_state.coords.shape == (nwalkers, ndim)
+    with pytest.raises(RuntimeError):
+        s.run_mcmc(coords, 2, skip_initial_state_check=True)
+
+
+def test_input_not_overwritten_and_resume():
+    # tests/unit/test_state.py:35-47, tests/unit/test_sampler.py:197-209
+    s = make(seed=7)
+    p0 = np.random.default_rng(4).standard_normal((32, 3))
+    keep = p0.copy()
+    s.run_mcmc(p0, 10)
+    assert np.array_equal(p0, keep)
+    s.run_mcmc(None, 10)
+    assert s.get_chain().shape == (20, 32, 3)
+    # a fresh sampler stepped 20 in one go gives the same chain (counter-based RNG)
+    s2 = make(seed=7)
+    s2.run_mcmc(p0, 20)
+    assert np.array_equal(s.get_chain(), s2.get_chain())
+
+
+def test_thin_by_equivalence():
+    # tests/unit/test_sampler.py:152-194
+    p0 = np.random.default_rng(5).standard_normal((32, 3))
+    a = make(seed=11)
+    a.run_mcmc(p0, 40)
+    b = make(seed=11)
+    b.run_mcmc(p0, 10, thin_by=4)
+    assert b.get_chain().shape == (10, 32, 3)
+    assert np.array_equal(a.get_chain()[3::4], b.get_chain())
+    assert np.array_equal(a.get_log_prob()[3::4], b.get_log_prob())
+    c = make(seed=11)
+    for _ in c.sample(p0, iterations=10, thin_by=4):
+        pass
+    assert np.array_equal(c.get_chain(), b.get_chain())
+    assert np.array_equal(c.backend.accepted, b.backend.accepted)
+
+
+def test_infinite_iteration_and_random_state():
+    # tests/unit/test_sampler.py:324-346
+    s = make(seed=3)
+    p0 = np.random.default_rng(6).standard_normal((32, 3))
+    for k, state in enumerate(s.sample(p0, iterations=None, store=False)):
+        if k == 9:
+            break
+    assert s.random_state == ("philox4x32-10", 3, 10)
+    s.random_state = "garbage"  # silently ignored, like ensemble.py:235-238
+    assert s.random_state[2] == 10
+    s.random_state = ("philox4x32-10", 3, 0)
+    assert s.random_state[2] == 0
+
+
+def _stat_check(mv, ndim=1, nwalkers=32, nsteps=2000, seed=1234, start="normal"):
+    """tests/integration/test_proposal.py:31-102 (_test_normal / _test_uniform)."""
+    from scipy import stats
+
+    rng = np.random.default_rng(seed)
+    p0 = rng.standard_normal((nwalkers, ndim)) if start == "normal" else rng.random((nwalkers, 1))
+    s = emcee_b200.EnsembleSampler(nwalkers, ndim, models.GaussianIso(), moves=mv, seed=seed)
+    s.run_mcmc(p0, nsteps, skip_initial_state_check=True)
+    acc = s.acceptance_fraction
+    assert np.all((acc < 0.9) * (acc > 0.1)), acc
+    samps = s.get_chain(flat=True)
+    if start == "normal":
+        assert np.all(np.abs(np.mean(samps, axis=0)) < 0.08)
+        assert np.all(np.abs(np.std(samps, axis=0) - 1) < 0.05)
+        if ndim == 1:
+            ks, _ = stats.kstest(samps[:, 0], "norm")
+            assert ks < 0.05
+    else:
+        rng.shuffle(samps)
+        ks, _ = stats.kstest(samps[::100, 0], "uniform")
+        assert ks > 0.1
+
+
+@pytest.mark.parametrize("mv,kw", [
+    (moves.StretchMove(), {}),
+    (moves.StretchMove(), {"ndim": 3}),
+    (moves.StretchMove(nsplits=5), {}),
+    (moves.DEMove(), {}),
+    (moves.DEMove(gamma0=1.0), {"ndim": 2}),
+    (moves.DESnookerMove(), {"nsteps": 4000}),
+])
+def test_normal_target_statistics(mv, kw):
+    # tests/integration/test_stretch.py:16-31, test_de.py:10-19, test_de_snooker.py:10-16
+    _stat_check(mv, **kw)
+
+
+@pytest.mark.parametrize("mv", [moves.StretchMove(), moves.DEMove(), moves.DESnookerMove()])
+def test_uniform_start_statistics(mv):
+    _stat_check(mv, start="uniform", nsteps=4000 if isinstance(mv, moves.DESnookerMove) else 2000)

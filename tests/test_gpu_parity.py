@@ -1,0 +1,130 @@
+"""Parity of the CUDA path (through the C ABI) with the golden vectors of the
+unmodified reference and with the oracle at larger sizes.
+
+Tolerances (fp64):
+  * complement indices, accept masks, accept counts ........ bit-exact
+  * stretch-move coordinates (sub, mul, sub, no FMA) ....... bit-exact
+  * log-probabilities ....................................... rtol 1e-12 (summation order differs)
+  * DE / snooker coordinates ................................ rtol 1e-12 (cos/log of Box-Muller,
+    BLAS dot order in the reference's per-walker snooker loop)
+"""
+import numpy as np
+import pytest
+
+from oracle import redblue as rb
+from oracle import targets as T
+
+from gpu_util import device_model, device_moves, golden_sampler, move_rows_from_oracle
+from util import golden_names, load_golden, oracle_sampler
+
+import emcee_b200
+
+pytestmark = pytest.mark.gpu
+
+LP_RTOL, LP_ATOL = 1e-12, 1e-12
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_chain(name):
+    g = load_golden(name)
+    s = golden_sampler(g)
+    nsteps = g["chain"].shape[0]
+    stretch_only = bool(np.all(g["moves"][:, 0] == 0))
+    k = 0
+    for state in s.sample(g["p0"], iterations=nsteps, skip_initial_state_check=True):
+        if k == 0:
+            pass
+        if stretch_only:
+            assert np.array_equal(state.coords, g["chain"][k]), (name, k)
+        else:
+            np.testing.assert_allclose(state.coords, g["chain"][k], rtol=1e-12, atol=1e-14, err_msg="%s step %d" % (name, k))
+        np.testing.assert_allclose(state.log_prob, g["log_prob"][k], rtol=LP_RTOL, atol=LP_ATOL)
+        k += 1
+    assert k == nsteps
+    assert np.array_equal(s.backend.accepted, g["accepted"].sum(axis=0))
+    np.testing.assert_allclose(s.get_chain(), g["chain"], rtol=1e-12, atol=1e-14)
+    assert s.random_state == ("philox4x32-10", int(g["seed"]), nsteps)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_run_mcmc_bulk(name):
+    """run_mcmc = one C-ABI call for the whole run; must equal the stepwise chain."""
+    g = load_golden(name)
+    s = golden_sampler(g)
+    nsteps = g["chain"].shape[0]
+    last = s.run_mcmc(g["p0"], nsteps, skip_initial_state_check=True)
+    np.testing.assert_allclose(s.get_chain(), g["chain"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(s.get_log_prob(), g["log_prob"], rtol=LP_RTOL, atol=LP_ATOL)
+    assert np.array_equal(s.backend.accepted, g["accepted"].sum(axis=0))
+    np.testing.assert_allclose(last.coords, g["chain"][-1], rtol=1e-12, atol=1e-14)
+    # store=False path gives the same final state
+    s2 = golden_sampler(g)
+    last2 = s2.run_mcmc(g["p0"], nsteps, skip_initial_state_check=True, store=False)
+    assert np.array_equal(last2.coords, last.coords) and np.array_equal(last2.log_prob, last.log_prob)
+    assert np.array_equal(s2._engine.naccepted(), g["accepted"].sum(axis=0).astype(np.uint64))
+
+
+def test_initial_log_prob_matches():
+    for name in golden_names():
+        g = load_golden(name)
+        s = golden_sampler(g)
+        lp, blobs = s.compute_log_prob(g["p0"])
+        assert blobs is None and lp.dtype == np.float64
+        np.testing.assert_allclose(lp, g["lp0"], rtol=LP_RTOL, atol=LP_ATOL)
+
+
+def test_draw_taps_bit_exact():
+    """rint / zz / accept uniforms of a half-step, against the oracle's taps."""
+    g = load_golden("stretch_dense_64x8")
+    o = oracle_sampler(g)
+    s = golden_sampler(g)
+    eng = s._engine
+    eng.set_option("debug_taps", 1)
+    eng.set_state(g["p0"])
+    sched = s._schedule()
+    for _ in range(5):
+        o.run(1)
+        eng.step(sched, 1)
+        taps = eng.debug_taps()  # last half-step = split 1
+        assert np.array_equal(taps["active"], o.taps["active"])
+        assert np.array_equal(taps["partners"][0], o.taps["partner"])
+        assert np.array_equal(taps["scalar"], o.taps["zz"])
+        assert np.array_equal(taps["u_accept"], o.taps["u_accept"])
+
+
+CASES = [
+    # name, N, D, moves, nsteps
+    ("gauss_dense", 4096, 128, [(rb.Stretch(), 1.0)], 12),
+    ("gauss_dense", 2048, 64, [(rb.Stretch(a=2.5, nsplits=3), 1.0)], 8),
+    ("gauss_dense", 1000, 24, [(rb.Stretch(randomize_split=False), 1.0)], 8),
+    ("gauss_iso", 512, 37, [(rb.Stretch(), 1.0)], 10),
+    ("ring", 16384, 32, [(rb.Stretch(), 1.0)], 8),
+    ("rosenbrock", 2048, 256, [(rb.DE(), 0.8), (rb.Snooker(), 0.2)], 12),
+    ("rosenbrock", 1024, 16, [(rb.DE(sigma=1e-3, gamma0=0.7), 1.0)], 8),
+    ("gauss_iso", 640, 5, [(rb.Snooker(gammas=1.2), 1.0)], 8),
+]
+
+
+@pytest.mark.parametrize("name,N,D,omoves,nsteps", CASES)
+def test_against_oracle(name, N, D, omoves, nsteps):
+    target, p0 = T.make_config(name, N, D)
+    seed = 0xB200 + N + D
+    o = rb.OracleSampler(N, D, target, omoves, seed=seed)
+    o.set_state(p0)
+    s = emcee_b200.EnsembleSampler(
+        N, D, device_model(name, target=target), moves=device_moves(move_rows_from_oracle(omoves)), seed=seed
+    )
+    stretch_only = all(m.kind == "stretch" for m, _ in omoves)
+    k = 0
+    for state in s.sample(p0, iterations=nsteps, skip_initial_state_check=True, store=False):
+        acc_o = o.run(1)
+        k += 1
+        if stretch_only:
+            assert np.array_equal(state.coords, o.coords), k
+        else:
+            np.testing.assert_allclose(state.coords, o.coords, rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(state.log_prob, o.log_prob, rtol=1e-11, atol=1e-11)
+    assert np.array_equal(s._engine.naccepted(), o.naccepted.astype(np.uint64))
+    # chain moments within 1e-6 relative (north_star): trivially true when the states agree
+    np.testing.assert_allclose(state.coords.mean(0), o.coords.mean(0), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(np.cov(state.coords.T), np.cov(o.coords.T), rtol=1e-6, atol=1e-9)
