@@ -5,7 +5,7 @@ set -u
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.txt 2>&1
-echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1 ; echo "exit $?" ; tail -5 $OUT/pytest_gpu.log
+echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1 ; echo "exit $?" ; tail -5 $OUT/pytest_gpu.log
 echo "== sanitizer" ; timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "golden_chain" > $OUT/sanitizer.log 2>&1 ; echo "exit $?" ; tail -4 $OUT/sanitizer.log
 echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1 ; echo "exit $?" ; tail -3 $OUT/smoke.log
 echo "== microbench" ; timeout 300 python - > $OUT/microbench.log 2>&1 <<'PY'
