@@ -24,24 +24,62 @@ pytestmark = pytest.mark.gpu
 LP_RTOL, LP_ATOL = 1e-12, 1e-12
 
 
+def _tols(g):
+    """(exact, rtol, atol) for free-running chains.  The snooker update divides by
+    |s - z| (de_snooker.py:42-43): last-bit differences in the dot products grow
+    by ~1.6x per step (the numpy oracle with einsum instead of per-row np.dot
+    drifts to 1e-8 after 40 steps against the reference itself), so free-running
+    snooker chains are compared loosely and every single step tightly
+    (test_golden_single_steps)."""
+    kinds = set(g["moves"][:, 0].astype(int))
+    if kinds == {0}:
+        return True, 0.0, 0.0
+    if 2 in kinds:
+        return False, 1e-5, 1e-6
+    return False, 1e-12, 1e-12
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_chain(name):
     g = load_golden(name)
     s = golden_sampler(g)
     nsteps = g["chain"].shape[0]
-    stretch_only = bool(np.all(g["moves"][:, 0] == 0))
+    exact, rtol, atol = _tols(g)
     k = 0
     for state in s.sample(g["p0"], iterations=nsteps, skip_initial_state_check=True):
-        if stretch_only:
+        if exact:
             assert np.array_equal(state.coords, g["chain"][k]), (name, k)
         else:
-            np.testing.assert_allclose(state.coords, g["chain"][k], rtol=1e-12, atol=1e-12, err_msg="%s step %d" % (name, k))
-        np.testing.assert_allclose(state.log_prob, g["log_prob"][k], rtol=LP_RTOL, atol=LP_ATOL)
+            np.testing.assert_allclose(state.coords, g["chain"][k], rtol=rtol, atol=atol, err_msg="%s step %d" % (name, k))
+        np.testing.assert_allclose(state.log_prob, g["log_prob"][k], rtol=max(rtol, LP_RTOL), atol=max(10 * atol, LP_ATOL))
         k += 1
     assert k == nsteps
     assert np.array_equal(s.backend.accepted, g["accepted"].sum(axis=0))
-    np.testing.assert_allclose(s.get_chain(), g["chain"], rtol=1e-12, atol=1e-12)
     assert s.random_state == ("philox4x32-10", int(g["seed"]), nsteps)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_single_steps(name):
+    """Every step on its own: start from the reference's state k-1, run step k,
+    compare with the reference's state k -- no error compounding, so the
+    tolerance is tight for every move (and exact for the stretch move)."""
+    g = load_golden(name)
+    s = golden_sampler(g)
+    eng, sched = s._engine, s._schedule()
+    exact = _tols(g)[0]
+    prev_c, prev_lp = g["p0"], g["lp0"]
+    for k in range(g["chain"].shape[0]):
+        eng.set_state(prev_c, prev_lp)
+        eng.set_rng(int(g["seed"]), k)
+        acc = eng.step(sched, 1)
+        coords, lp = eng.get_state()
+        assert np.array_equal(acc, g["accepted"][k]), (name, k)
+        if exact:
+            assert np.array_equal(coords, g["chain"][k]), (name, k)
+        else:
+            np.testing.assert_allclose(coords, g["chain"][k], rtol=1e-12, atol=1e-12, err_msg="%s step %d" % (name, k))
+        np.testing.assert_allclose(lp, g["log_prob"][k], rtol=LP_RTOL, atol=LP_ATOL)
+        prev_c, prev_lp = g["chain"][k], g["log_prob"][k]
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -50,11 +88,12 @@ def test_golden_run_mcmc_bulk(name):
     g = load_golden(name)
     s = golden_sampler(g)
     nsteps = g["chain"].shape[0]
+    exact, rtol, atol = _tols(g)
     last = s.run_mcmc(g["p0"], nsteps, skip_initial_state_check=True)
-    np.testing.assert_allclose(s.get_chain(), g["chain"], rtol=1e-12, atol=1e-12)
-    np.testing.assert_allclose(s.get_log_prob(), g["log_prob"], rtol=LP_RTOL, atol=LP_ATOL)
+    np.testing.assert_allclose(s.get_chain(), g["chain"], rtol=rtol, atol=atol)
+    np.testing.assert_allclose(s.get_log_prob(), g["log_prob"], rtol=max(rtol, LP_RTOL), atol=max(10 * atol, LP_ATOL))
     assert np.array_equal(s.backend.accepted, g["accepted"].sum(axis=0))
-    np.testing.assert_allclose(last.coords, g["chain"][-1], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(last.coords, s.get_chain()[-1])
     # store=False path gives the same final state
     s2 = golden_sampler(g)
     last2 = s2.run_mcmc(g["p0"], nsteps, skip_initial_state_check=True, store=False)
@@ -113,6 +152,8 @@ def test_against_oracle(name, N, D, omoves, nsteps):
         N, D, device_model(name, target=target), moves=device_moves(move_rows_from_oracle(omoves)), seed=seed
     )
     stretch_only = all(m.kind == "stretch" for m, _ in omoves)
+    snooker = any(m.kind == "snooker" for m, _ in omoves)
+    tol = 1e-6 if snooker else 1e-11  # free-running snooker chains amplify last-bit differences (see _tols)
     k = 0
     for state in s.sample(p0, iterations=nsteps, skip_initial_state_check=True, store=False):
         acc_o = o.run(1)
@@ -120,8 +161,8 @@ def test_against_oracle(name, N, D, omoves, nsteps):
         if stretch_only:
             assert np.array_equal(state.coords, o.coords), k
         else:
-            np.testing.assert_allclose(state.coords, o.coords, rtol=1e-11, atol=1e-11)
-        np.testing.assert_allclose(state.log_prob, o.log_prob, rtol=1e-11, atol=1e-11)
+            np.testing.assert_allclose(state.coords, o.coords, rtol=tol, atol=tol)
+        np.testing.assert_allclose(state.log_prob, o.log_prob, rtol=max(tol, 1e-11), atol=max(100 * tol, 1e-11))
     assert np.array_equal(s._engine.naccepted(), o.naccepted.astype(np.uint64))
     # chain moments within 1e-6 relative (north_star): trivially true when the states agree
     np.testing.assert_allclose(state.coords.mean(0), o.coords.mean(0), rtol=1e-6, atol=1e-9)
