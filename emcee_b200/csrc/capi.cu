@@ -264,6 +264,8 @@ int eb_model_set(eb_ctx* c, int kind, const double* params, size_t nparams) {
       for (size_t k = 0; k < nparams; ++k)
         if (!isfinite(params[k])) FAIL(c, EB_ERR_INVALID, "gauss_dense parameters must be finite");
       host.assign(params, params + nparams);
+      for (size_t k = 0; k < D; ++k)
+        if (params[k] != 0.0) m.s0 = 1.0;  // non-zero mean (dense_dmma.cu picks its variant by this)
       break;
     case EB_MODEL_ROSENBROCK:
     case EB_MODEL_RING:
