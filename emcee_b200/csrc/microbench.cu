@@ -96,6 +96,62 @@ __global__ void dmma16816_kernel(double* out, int iters, double x, double y) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// the consumer loop of dense_dmma.cu in isolation: B fragments streamed from shared
+// memory (one LDS per DMMA), A fragments from 32 different registers, CH independent
+// accumulator chains
+template <int CH>
+__global__ void dmma884_smem_kernel(double* out, int iters, double x) {
+  extern __shared__ double sb[];
+  for (int k = threadIdx.x; k < 8704; k += blockDim.x) sb[k] = 1e-9 * k;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  double a[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) a[k] = x + 1e-9 * (k + lane);
+  double c0[CH], c1[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) c0[k] = c1[k] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+    const double* bp = sb + lane;
+#pragma unroll
+    for (int j = 0; j < 256; ++j) {
+      dmma884(c0[j % CH], c1[j % CH], a[j % 32], bp[32 * j]);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) s += c0[k] + c1[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int CH>
+__global__ void dmma1688_smem_kernel(double* out, int iters, double x) {
+  extern __shared__ double sb[];
+  for (int k = threadIdx.x; k < 8704; k += blockDim.x) sb[k] = 1e-9 * k;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  double a[16][4];
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    for (int m = 0; m < 4; ++m) a[k][m] = x + 1e-9 * (k + m + lane);
+  double c[CH][4];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) c[k][0] = c[k][1] = c[k][2] = c[k][3] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+    const double* bp = sb + 2 * lane;
+#pragma unroll
+    for (int j = 0; j < 128; ++j) {
+      const double2 b2 = *reinterpret_cast<const double2*>(bp + 64 * j);
+      const double b[2] = {b2.x, b2.y};
+      dmma1688(c[j % CH], a[j % 16], b);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) s += c[k][0] + c[k][1] + c[k][2] + c[k][3];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = src[i];
@@ -158,6 +214,27 @@ extern "C" int eb_microbench(int what, int warps_per_sm, double* result) {
       ms = time_ms([&] { dmma16816_kernel<ILP><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); }, 5);
       flops = nwarps * ILP * iters * 4096.0;
       break;
+    case 5:  // DMMA m8n8k4, B from shared memory, 8 chains (dense_dmma consumer loop)
+    case 6:  // same, 4 chains
+    case 7:  // DMMA m16n8k8, B from shared memory, 4 chains
+    case 8: {  // same, 2 chains
+      const int it2 = 64;
+      const size_t smem = 8704 * sizeof(double);
+      cudaFuncSetAttribute(dmma884_smem_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(dmma884_smem_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(dmma1688_smem_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(dmma1688_smem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (what == 5)
+        ms = time_ms([&] { dmma884_smem_kernel<8><<<blocks, threads, smem>>>(out, it2, 1.0000001); }, 5);
+      else if (what == 6)
+        ms = time_ms([&] { dmma884_smem_kernel<4><<<blocks, threads, smem>>>(out, it2, 1.0000001); }, 5);
+      else if (what == 7)
+        ms = time_ms([&] { dmma1688_smem_kernel<4><<<blocks, threads, smem>>>(out, it2, 1.0000001); }, 5);
+      else
+        ms = time_ms([&] { dmma1688_smem_kernel<2><<<blocks, threads, smem>>>(out, it2, 1.0000001); }, 5);
+      flops = nwarps * it2 * (what <= 6 ? 256 * 512.0 : 128 * 2048.0);
+      break;
+    }
     case 4: {  // HBM copy, 1 GiB read + 1 GiB write
       const size_t n = (size_t)1 << 26;  // double2 elements = 1 GiB
       double2 *a = nullptr, *b = nullptr;
