@@ -133,54 +133,6 @@ class ClockSampler(object):
         return out
 
 
-class Dist(object):
-    """torch.distributed (gloo) as host-side plumbing only: broadcast of the
-    NCCL id / IPC handles, barrier, max over ranks.  The data path never touches torch."""
-
-    def __init__(self):
-        self.rank = int(os.environ.get("RANK", "0"))
-        self.world = int(os.environ.get("WORLD_SIZE", "1"))
-        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-        self.td = None
-        if self.world > 1:
-            import torch.distributed as td
-
-            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            td.init_process_group("gloo", rank=self.rank, world_size=self.world)
-            self.td = td
-
-    def barrier(self):
-        if self.td:
-            self.td.barrier()
-
-    def bcast_bytes(self, data, src=0):
-        if not self.td:
-            return data
-        box = [data]
-        self.td.broadcast_object_list(box, src=src)
-        return box[0]
-
-    def allgather_bytes(self, data):
-        if not self.td:
-            return [data]
-        out = [None] * self.world
-        self.td.all_gather_object(out, data)
-        return out
-
-    def max(self, x):
-        if not self.td:
-            return x
-        import torch
-
-        t = torch.tensor([x], dtype=torch.float64)
-        self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
-        return float(t[0])
-
-    def close(self):
-        if self.td:
-            self.td.destroy_process_group()
-
-
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -289,15 +241,12 @@ def run_b200(args, dist):
     }[w["name"]]()
     mv = moves.StretchMove() if w["moves"] == "stretch" else [(moves.DEMove(), 0.8), (moves.DESnookerMove(), 0.2)]
 
-    sampler = emcee_b200.EnsembleSampler(n_total, D, model, moves=mv, seed=SAMPLER_SEED, device=dist.local_rank)
+    sampler = emcee_b200.EnsembleSampler(n_total, D, model, moves=mv, seed=SAMPLER_SEED, device=dist.local_rank,
+                                        pinned_results=True)
     eng = sampler._engine
-    if world > 1:
-        mode = _lib.EB_COMM_P2P if args.comm == "p2p" else _lib.EB_COMM_ALLGATHER
-        cid = dist.bcast_bytes(_lib.Engine.comm_id() if dist.rank == 0 else None)
-        eng.comm_init(cid, dist.rank, world, mode)
-        if mode == _lib.EB_COMM_P2P:
-            blobs = dist.allgather_bytes(eng.comm_export())
-            eng.comm_import(b"".join(blobs))
+    from emcee_b200 import dist as ebdist
+
+    ebdist.attach(eng, dist, args.comm)
     eng.set_option("l2_flush", 1 if args.l2_flush else 0)
     sched = sampler._schedule()
 
@@ -410,7 +359,9 @@ def main():
         if args.l2_flush else
         "no flush: the ensemble (N*D*8 B) stays L2-resident across steps, as it does in a real run"
     )
-    dist = Dist()
+    from emcee_b200.dist import Rendezvous
+
+    dist = Rendezvous("gloo")
     if dist.world != args.gpus and dist.world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, dist.world))
     try:

@@ -212,9 +212,13 @@ class Engine(object):
         lp = None if log_prob is None else _f64(log_prob, (self.nwalkers,))
         self._check(lib().eb_set_state(self._h, _as_dp(coords), None if lp is None else _as_dp(lp)))
 
-    def get_state(self):
-        coords = np.empty((self.nwalkers, self.ndim), dtype=np.float64)
-        lp = np.empty(self.nwalkers, dtype=np.float64)
+    def get_state(self, coords=None, log_prob=None):
+        """Device -> host copy of the live state, into fresh arrays or into the
+        given (C-contiguous float64, e.g. pinned) buffers."""
+        coords = np.empty((self.nwalkers, self.ndim), dtype=np.float64) if coords is None else coords
+        lp = np.empty(self.nwalkers, dtype=np.float64) if log_prob is None else log_prob
+        assert coords.flags.c_contiguous and coords.dtype == np.float64 and coords.shape == (self.nwalkers, self.ndim)
+        assert lp.flags.c_contiguous and lp.dtype == np.float64 and lp.shape == (self.nwalkers,)
         self._check(lib().eb_get_state(self._h, _as_dp(coords), _as_dp(lp)))
         return coords, lp
 

@@ -99,6 +99,7 @@ static int check_status(eb_ctx* c) {
   *c->status_host = 0;
   cudaMemsetAsync(c->status_dev, 0, sizeof(int), c->st);
   cudaStreamSynchronize(c->st);
+  if (f & FLAG_COMM_TIMEOUT) FAIL(c, EB_ERR_COMM, "peer-memory barrier timed out: another rank did not arrive");
   if (f & FLAG_INF_PARAM) FAIL(c, EB_ERR_INF_PARAM, "At least one parameter value was infinite");
   if (f & FLAG_NAN_PARAM) FAIL(c, EB_ERR_NAN_PARAM, "At least one parameter value was NaN");
   FAIL(c, EB_ERR_NAN_LOGPROB, "Probability function returned NaN");
@@ -167,7 +168,8 @@ int eb_create(int device, int64_t nwalkers, int64_t ndim, uint64_t seed, eb_ctx*
   CC(cudaEventCreate(&c->ev0));
   CC(cudaEventCreate(&c->ev1));
   const size_t nd = (size_t)nwalkers * (size_t)ndim;
-  CC(cudaMalloc(&c->coords, nd * sizeof(double)));
+  // the tail holds the peer-memory barrier flags so one IPC handle exports both
+  CC(cudaMalloc(&c->coords, nd * sizeof(double) + MAX_RANKS * sizeof(unsigned)));
   CC(cudaMalloc(&c->logp, (size_t)nwalkers * sizeof(double)));
   CC(cudaMalloc(&c->accepted, (size_t)nwalkers));
   CC(cudaMalloc(&c->nacc, (size_t)nwalkers * sizeof(unsigned long long)));
@@ -437,7 +439,8 @@ size_t choose_move(const eb_ctx* c, const Schedule& s, uint64_t step) {
 }
 
 // launch the P half-steps of one step
-int launch_step(eb_ctx* c, const eb_move& mv, uint64_t step, const int32_t* order, uint64_t& launches) {
+int launch_step(eb_ctx* c, const eb_move& mv, uint64_t step, const int32_t* order, size_t step_in_chunk,
+                uint64_t& launches) {
   const int P = mv.nsplits;
   const int64_t N = c->N;
   if (N < 2 * (int64_t)c->D && !mv.live_dangerously)  // red_blue.py:64-70
@@ -490,8 +493,8 @@ int launch_step(eb_ctx* c, const eb_move& mv, uint64_t step, const int32_t* orde
       a.c_count[k] = start[j + 1] - start[j];
       ++k;
     }
-    int rc = comm_active_range(c->comm, c->st, a, order);  // i_lo / i_hi for this rank
-    if (rc) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+    comm_active_range(c->comm, a, step_in_chunk);  // i_lo / i_hi for this rank
+    int rc;
     if (dmma) {
       CK(c, launch_half_step_dense_dmma(a, c->sm_count, c->st));
       c->last_kernel = "dense_dmma";
@@ -501,7 +504,7 @@ int launch_step(eb_ctx* c, const eb_move& mv, uint64_t step, const int32_t* orde
     }
     ++launches;
     c->tap_count = a.a_count;
-    rc = comm_after_split(c->comm, c->st, a, launches);  // exchange the updated rows
+    rc = comm_after_split(c->comm, c->st, c->status_dev, launches);  // exchange the updated rows
     if (rc) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
   }
   return EB_OK;
@@ -523,6 +526,7 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, F&& after_step) {
     }
   }
   CK(c, cudaEventRecord(c->ev0, c->st));
+  if (comm_begin(c->comm, c->st, c->status_dev, launches)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
   std::vector<size_t> pick;
   uint64_t done = 0;
   while (done < nsteps) {
@@ -542,10 +546,13 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, F&& after_step) {
       if (k == 0) {
         // split tables of the whole chunk (charged to the chunk's first step)
         CK(c, cudaMemcpyAsync(c->info_dev, c->info_host, chunk * sizeof(StepInfo), cudaMemcpyHostToDevice, c->st));
-        CK(c, launch_split_tables(c->order, c->info_dev, (int)chunk, c->N, c->seed, c->step, c->st));
+        const Comm& cm = c->comm;
+        CK(c, launch_split_tables(c->order, c->info_dev, (int)chunk, c->N, c->seed, c->step,
+                                  cm.rows_per_rank * cm.rank, cm.rows_per_rank * (cm.rank + 1),
+                                  cm.nranks > 1 ? cm.ranges : nullptr, c->st));
         ++launches;
       }
-      int rc = launch_step(c, s.moves[pick[k]], c->step, c->order + k * (size_t)c->N, launches);
+      int rc = launch_step(c, s.moves[pick[k]], c->step, c->order + k * (size_t)c->N, k, launches);
       if (rc) return rc;
       c->step += 1;
       if (perstep) CK(c, cudaEventRecord(c->ev_pool[2 * (done + k) + 1], c->st));
@@ -555,6 +562,10 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, F&& after_step) {
     done += chunk;
   }
   CK(c, cudaEventRecord(c->ev1, c->st));
+  // replicate log_prob / accept mask / counters across ranks (outside the timed bracket: it is
+  // bookkeeping for eb_get_state, not part of a step)
+  if (comm_sync_state(c->comm, c->st, c->status_dev, c->logp, c->accepted, c->nacc, launches))
+    FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
   CK(c, cudaMemcpyAsync(c->status_host, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   CK(c, cudaStreamSynchronize(c->st));
   float ms = 0.f;
@@ -744,7 +755,9 @@ int eb_comm_id(char id[EB_COMM_ID_BYTES]) { return comm_unique_id(id) ? EB_ERR_C
 int eb_comm_init(eb_ctx* c, const char id[EB_COMM_ID_BYTES], int rank, int nranks, int mode) {
   if (!c) return EB_ERR_INVALID;
   CK(c, cudaSetDevice(c->device));
-  if (comm_init(c->comm, id, rank, nranks, mode, c->N, c->D, c->coords, c->st)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+  unsigned* flags = reinterpret_cast<unsigned*>(c->coords + (size_t)c->N * c->D);
+  if (comm_init(c->comm, id, rank, nranks, mode, c->N, c->D, c->coords, flags, c->table_cap, c->st))
+    FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
   return EB_OK;
 }
 

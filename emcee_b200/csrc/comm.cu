@@ -1,52 +1,257 @@
-// Multi-GPU plumbing (see comm.h).  Phase 1: single rank only.
+// Multi-GPU plumbing (see comm.h): one process per GPU, walkers sharded by row block.
+//
+// The reference's only parallel construct is pool.map over the proposals of one
+// split (ensemble.py:492-496); what makes that legal -- the complement is frozen
+// while a split is updated (red_blue.py:85-104) -- is what makes row-block
+// sharding legal here: a rank updates the active walkers it owns and only READS
+// complement rows, which other ranks do not write during the split.
+//
+//   EB_COMM_ALLGATHER  every rank holds a replica of coords; after each split the
+//                      owned row blocks are all-gathered in place (ncclAllGather,
+//                      NCCL dlopen-ed: single-GPU use never loads it).
+//   EB_COMM_P2P        no replica traffic: the half-step kernel reads partner rows
+//                      straight from the owner's HBM over NVLink through
+//                      cudaIpc-mapped pointers (HalfStepArgs::peer_coords), and the
+//                      ranks meet at a flag barrier in peer memory between splits.
 #include "comm.h"
 
+#include <dlfcn.h>
+#include <nccl.h>  // types only; every entry point is resolved with dlsym
+#include <stdio.h>
 #include <string.h>
 
 namespace eb {
 
-int comm_unique_id(char* id128) {
-  memset(id128, 0, EB_COMM_ID_BYTES);
+namespace {
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+};
+
+NcclApi& nccl_api() {
+  static NcclApi api;
+  if (api.lib || !api.err.empty()) return api;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) {
+    api.err = std::string("cannot load libnccl.so.2: ") + dlerror();
+    return api;
+  }
+#define LOAD(field, sym)                                                    \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, sym));   \
+  if (!api.field) api.err = std::string("libnccl lacks ") + sym;
+  LOAD(GetUniqueId, "ncclGetUniqueId")
+  LOAD(CommInitRank, "ncclCommInitRank")
+  LOAD(AllGather, "ncclAllGather")
+  LOAD(CommDestroy, "ncclCommDestroy")
+  LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+  return api;
+}
+
+static_assert(sizeof(ncclUniqueId) == EB_COMM_ID_BYTES, "EB_COMM_ID_BYTES must match ncclUniqueId");
+
+struct IpcBlob {
+  cudaIpcMemHandle_t mem;  // the coords allocation (flags live in its tail)
+  int32_t rank;
+  int32_t pad;
+};
+static_assert(sizeof(IpcBlob) <= EB_IPC_BLOB_BYTES, "IPC blob too large");
+
+// cross-GPU barrier: publish my epoch into every peer's flag array, then wait until
+// every peer has published theirs into mine.  Launched on the engine's stream after
+// the half-step kernel, so all of that kernel's writes precede the release.
+__global__ void p2p_barrier_kernel(unsigned* const* peer_flags, volatile unsigned* my_flags, int rank, int nranks,
+                                   unsigned epoch, int* status) {
+  const int t = threadIdx.x;
+  if (t < nranks) {
+    __threadfence_system();
+    atomicExch_system(peer_flags[t] + rank, epoch);
+    const long long t0 = clock64();
+    while ((int)(my_flags[t] - epoch) < 0) {
+      __nanosleep(64);
+      if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died; report instead of hanging the GPU
+        atomicOr(status, FLAG_COMM_TIMEOUT);
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+}
+
+int fail(Comm& c, const std::string& msg) {
+  c.err = msg;
   return 1;
 }
 
-int comm_init(Comm& c, const char*, int rank, int nranks, int mode, int64_t N, int D, double* coords,
-              cudaStream_t) {
-  if (nranks != 1 || rank != 0) {
-    c.err = "multi-GPU communicator not built yet";
-    return 1;
-  }
-  c.rank = 0;
-  c.nranks = 1;
+#define CCK(c, call)                                                                        \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      cudaGetLastError();                                                                   \
+      return fail(c, std::string(#call) + " failed: " + cudaGetErrorString(_e));            \
+    }                                                                                       \
+  } while (0)
+
+#define NCK(c, call)                                                                        \
+  do {                                                                                      \
+    ncclResult_t _r = (call);                                                               \
+    if (_r != ncclSuccess) return fail(c, std::string(#call) + " failed: " + nccl_api().GetErrorString(_r)); \
+  } while (0)
+
+}  // namespace
+
+int comm_unique_id(char* id128) {
+  NcclApi& api = nccl_api();
+  if (!api.err.empty()) return 1;
+  ncclUniqueId id;
+  if (api.GetUniqueId(&id) != ncclSuccess) return 1;
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int comm_init(Comm& c, const char* id128, int rank, int nranks, int mode, int64_t N, int D, double* coords,
+              unsigned* flags, size_t table_cap, cudaStream_t st) {
+  if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) return fail(c, "comm_init: bad rank / nranks");
+  if (N % nranks != 0) return fail(c, "comm_init: nwalkers must be divisible by the number of ranks");
+  if (mode != EB_COMM_ALLGATHER && mode != EB_COMM_P2P) return fail(c, "comm_init: unknown mode");
+  c.rank = rank;
+  c.nranks = nranks;
   c.mode = mode;
   c.N = N;
   c.D = D;
   c.coords = coords;
-  c.rows_per_rank = N;
+  c.flags = flags;
+  c.rows_per_rank = N / nranks;
+  if (nranks == 1) return 0;
+  NcclApi& api = nccl_api();
+  if (!api.err.empty()) return fail(c, api.err);
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm = nullptr;
+  NCK(c, api.CommInitRank(&comm, nranks, id, rank));
+  c.nccl = comm;
+  CCK(c, cudaMalloc(&c.ranges, table_cap * MAX_SPLITS * sizeof(int2)));
+  CCK(c, cudaMemsetAsync(c.flags, 0, MAX_RANKS * sizeof(unsigned), st));
+  CCK(c, cudaStreamSynchronize(st));
   return 0;
 }
 
-int comm_export(Comm& c, char*) {
-  c.err = "peer memory not built yet";
-  return 1;
-}
-int comm_import(Comm& c, const char*) {
-  c.err = "peer memory not built yet";
-  return 1;
-}
-void comm_destroy(Comm&) {}
-
-void comm_fill_args(const Comm&, HalfStepArgs& a) {
-  a.peer_coords = nullptr;
-  a.rows_per_rank = a.N;
+int comm_export(Comm& c, char* blob) {
+  memset(blob, 0, EB_IPC_BLOB_BYTES);
+  IpcBlob b;
+  memset(&b, 0, sizeof(b));
+  CCK(c, cudaIpcGetMemHandle(&b.mem, c.coords));
+  b.rank = c.rank;
+  memcpy(blob, &b, sizeof(b));
+  return 0;
 }
 
-int comm_active_range(Comm&, cudaStream_t, HalfStepArgs& a, const int32_t*) {
+int comm_import(Comm& c, const char* blobs) {
+  if (c.nranks == 1) return 0;
+  const double* coords_host[MAX_RANKS];
+  unsigned* flags_host[MAX_RANKS];
+  const size_t flag_off = (size_t)c.N * c.D;  // flags sit right behind the coords in the same allocation
+  for (int r = 0; r < c.nranks; ++r) {
+    IpcBlob b;
+    memcpy(&b, blobs + (size_t)r * EB_IPC_BLOB_BYTES, sizeof(b));
+    if (b.rank != r) return fail(c, "comm_import: blobs are not ordered by rank");
+    void* base = nullptr;
+    if (r == c.rank) {
+      base = c.coords;
+    } else {
+      CCK(c, cudaIpcOpenMemHandle(&base, b.mem, cudaIpcMemLazyEnablePeerAccess));
+      c.peer_base[r] = base;
+    }
+    coords_host[r] = static_cast<const double*>(base);
+    flags_host[r] = reinterpret_cast<unsigned*>(static_cast<double*>(base) + flag_off);
+  }
+  CCK(c, cudaMalloc(&c.peer_coords_dev, c.nranks * sizeof(double*)));
+  CCK(c, cudaMalloc(&c.peer_flags_dev, c.nranks * sizeof(unsigned*)));
+  CCK(c, cudaMemcpy(c.peer_coords_dev, coords_host, c.nranks * sizeof(double*), cudaMemcpyHostToDevice));
+  CCK(c, cudaMemcpy(c.peer_flags_dev, flags_host, c.nranks * sizeof(unsigned*), cudaMemcpyHostToDevice));
+  c.imported = true;
+  return 0;
+}
+
+void comm_destroy(Comm& c) {
+  for (int r = 0; r < MAX_RANKS; ++r)
+    if (c.peer_base[r]) cudaIpcCloseMemHandle(c.peer_base[r]);
+  cudaFree(c.peer_coords_dev);
+  cudaFree(c.peer_flags_dev);
+  cudaFree(c.ranges);
+  if (c.nccl) nccl_api().CommDestroy(static_cast<ncclComm_t>(c.nccl));
+  c = Comm();
+}
+
+void comm_fill_args(const Comm& c, HalfStepArgs& a) {
+  a.rows_per_rank = c.rows_per_rank > 0 ? c.rows_per_rank : a.N;
+  a.peer_coords = (c.nranks > 1 && c.mode == EB_COMM_P2P) ? c.peer_coords_dev : nullptr;
+}
+
+void comm_active_range(const Comm& c, HalfStepArgs& a, size_t step_in_chunk) {
   a.i_lo = 0;
-  a.i_hi = a.a_count;
+  if (c.nranks == 1) {
+    a.i_hi = a.a_count;
+    a.range = nullptr;
+    return;
+  }
+  // the exact range is device resident (split_table_kernel); the host only needs a bound for the grid
+  a.i_hi = (int)(a.a_count < c.rows_per_rank ? a.a_count : c.rows_per_rank);
+  a.range = c.ranges + step_in_chunk * MAX_SPLITS + a.split;
+}
+
+static int p2p_barrier(Comm& c, cudaStream_t st, int* status, uint64_t& launches) {
+  if (!c.imported) return fail(c, "EB_COMM_P2P: eb_comm_import has not been called");
+  c.epoch += 1;
+  p2p_barrier_kernel<<<1, 32, 0, st>>>(c.peer_flags_dev, c.flags, c.rank, c.nranks, c.epoch, status);
+  CCK(c, cudaGetLastError());
+  ++launches;
   return 0;
 }
 
-int comm_after_split(Comm&, cudaStream_t, const HalfStepArgs&, uint64_t&) { return 0; }
+int comm_begin(Comm& c, cudaStream_t st, int* status, uint64_t& launches) {
+  if (c.nranks == 1 || c.mode != EB_COMM_P2P) return 0;
+  return p2p_barrier(c, st, status, launches);
+}
+
+int comm_after_split(Comm& c, cudaStream_t st, int* status, uint64_t& launches) {
+  if (c.nranks == 1) return 0;
+  if (c.mode == EB_COMM_ALLGATHER) {
+    const size_t cnt = (size_t)c.rows_per_rank * c.D;
+    NCK(c, nccl_api().AllGather(c.coords + (size_t)c.rank * cnt, c.coords, cnt, ncclDouble,
+                                static_cast<ncclComm_t>(c.nccl), st));
+    ++launches;
+    return 0;
+  }
+  return p2p_barrier(c, st, status, launches);
+}
+
+int comm_sync_state(Comm& c, cudaStream_t st, int* status, double* logp, uint8_t* accepted,
+                    unsigned long long* nacc, uint64_t& launches) {
+  if (c.nranks == 1) return 0;
+  NcclApi& api = nccl_api();
+  ncclComm_t comm = static_cast<ncclComm_t>(c.nccl);
+  const size_t R = (size_t)c.rows_per_rank;
+  if (c.mode == EB_COMM_P2P) {  // replicas were not maintained during the run
+    NCK(c, api.AllGather(c.coords + (size_t)c.rank * R * c.D, c.coords, R * c.D, ncclDouble, comm, st));
+    ++launches;
+  }
+  NCK(c, api.AllGather(logp + c.rank * R, logp, R, ncclDouble, comm, st));
+  NCK(c, api.AllGather(accepted + c.rank * R, accepted, R, ncclUint8, comm, st));
+  NCK(c, api.AllGather(nacc + c.rank * R, nacc, R, ncclUint64, comm, st));
+  launches += 3;
+  if (c.mode == EB_COMM_P2P) return p2p_barrier(c, st, status, launches);  // gathers landed everywhere
+  return 0;
+}
 
 }  // namespace eb

@@ -23,16 +23,14 @@ struct Comm {
   int64_t N = 0;
   int D = 0;
   int64_t rows_per_rank = 0;
-  double* coords = nullptr;  // this rank's [N, D] buffer
-  // NCCL (dlopen)
-  void* lib = nullptr;
-  void* nccl = nullptr;
+  double* coords = nullptr;   // this rank's [N, D] buffer (+ barrier flags in its tail)
+  unsigned* flags = nullptr;  // this rank's barrier flags [MAX_RANKS], inside the coords allocation
+  int2* ranges = nullptr;     // [table_cap, MAX_SPLITS] active-rank range of this rank per (step, set)
+  void* nccl = nullptr;       // ncclComm_t
   // P2P
   void* peer_base[MAX_RANKS] = {nullptr};
-  const double** peer_coords_dev = nullptr;   // device array [nranks]
-  unsigned* flags = nullptr;                  // this rank's barrier flags [MAX_RANKS] (device, exported)
-  unsigned* peer_flags[MAX_RANKS] = {nullptr};
-  unsigned** peer_flags_dev = nullptr;
+  const double** peer_coords_dev = nullptr;  // device array [nranks]
+  unsigned** peer_flags_dev = nullptr;       // device array [nranks]
   unsigned epoch = 0;
   bool imported = false;
   std::string err;
@@ -40,15 +38,20 @@ struct Comm {
 
 int comm_unique_id(char* id128);
 int comm_init(Comm& c, const char* id128, int rank, int nranks, int mode, int64_t N, int D, double* coords,
-              cudaStream_t st);
+              unsigned* flags, size_t table_cap, cudaStream_t st);
 int comm_export(Comm& c, char* blob);
 int comm_import(Comm& c, const char* blobs);
 void comm_destroy(Comm& c);
 // peer pointers / ownership for the kernels
 void comm_fill_args(const Comm& c, HalfStepArgs& a);
-// [i_lo, i_hi): the active ranks of this split owned by this rank
-int comm_active_range(Comm& c, cudaStream_t st, HalfStepArgs& a, const int32_t* order);
+// [i_lo, i_hi): the active ranks of this split owned by this rank (device resident when nranks > 1)
+void comm_active_range(const Comm& c, HalfStepArgs& a, size_t step_in_chunk);
+// P2P: all ranks rendezvous before the first split of a call
+int comm_begin(Comm& c, cudaStream_t st, int* status, uint64_t& launches);
 // make the rows updated in this split visible to every rank
-int comm_after_split(Comm& c, cudaStream_t st, const HalfStepArgs& a, uint64_t& launches);
+int comm_after_split(Comm& c, cudaStream_t st, int* status, uint64_t& launches);
+// end of a stepping call: replicate log_prob / accept mask / counters (and coords in P2P mode)
+int comm_sync_state(Comm& c, cudaStream_t st, int* status, double* logp, uint8_t* accepted,
+                    unsigned long long* nacc, uint64_t& launches);
 
 }  // namespace eb

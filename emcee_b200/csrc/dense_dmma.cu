@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1) half_step_dense_dmma_kernel(c
       for (int k = tid; k < D; k += DMMA_THREADS) sMu[k] = a.model.params[k];
   }
 
-  const int64_t count = (int64_t)a.i_hi - a.i_lo;
+  const int i_lo = a.range ? a.range->x : a.i_lo;
+  const int i_hi = a.range ? a.range->y : a.i_hi;
+  const int64_t count = (int64_t)i_hi - i_lo;
   const int64_t ntiles = (count + 7) >> 3;
   const int64_t Nc = a.N - a.a_count;
   const double dm1 = (double)a.D - 1.0;
@@ -100,9 +102,9 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1) half_step_dense_dmma_kernel(c
   // draws + index lookups of one tile (stretch.py:30-32, red_blue.py:82-87,100)
   auto prep = [&](int64_t tile) -> TileMeta {
     TileMeta m;
-    int64_t i = (int64_t)a.i_lo + tile * 8 + g;
-    m.valid = i < a.i_hi;
-    if (!m.valid) i = (int64_t)a.i_hi - 1;
+    int64_t i = (int64_t)i_lo + tile * 8 + g;
+    m.valid = i < i_hi;
+    if (!m.valid) i = (int64_t)i_hi - 1;
     const u32x4 A = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_PROP_A, (uint32_t)i);
     const double tt = __dadd_rn(__dmul_rn(__dsub_rn(a.p0, 1.0), u53(A.x, A.y)), 1.0);
     m.zz = __ddiv_rn(__dmul_rn(tt, tt), a.p0);

@@ -19,6 +19,7 @@ enum : int {
   FLAG_NAN_LOGPROB = 1,
   FLAG_INF_PARAM = 2,
   FLAG_NAN_PARAM = 4,
+  FLAG_COMM_TIMEOUT = 8,
 };
 
 struct ModelDev {
@@ -48,7 +49,8 @@ struct HalfStepArgs {
   int D;
   int split;
   int a_start, a_count;  // active set = order[a_start .. a_start + a_count)
-  int i_lo, i_hi;        // active ranks processed by this GPU
+  int i_lo, i_hi;        // active ranks processed by this GPU (an upper bound for grid sizing when `range` is set)
+  const int2* range;     // multi-GPU: device-resident [i_lo, i_hi) of this rank for this (step, split), or null
   int c_start[3], c_count[3];  // snooker: the three complement sets (ascending j != split)
   uint64_t seed, step;
   double p0, p1;  // stretch: a | de: g0, sigma | snooker: gammas
@@ -63,8 +65,10 @@ struct HalfStepArgs {
 struct Engine;  // defined in capi.cu
 
 // ---- kernel launchers (implemented in the .cu files) ----------------------
+// ranges (nullable): [nsteps_chunk, MAX_SPLITS] int2 = active ranks of each set owned by walkers [w_lo, w_hi)
 cudaError_t launch_split_tables(int32_t* order, const StepInfo* info_dev, int nsteps_chunk, int64_t N,
-                                uint64_t seed, uint64_t step0, cudaStream_t st);
+                                uint64_t seed, uint64_t step0, int64_t w_lo, int64_t w_hi, int2* ranges,
+                                cudaStream_t st);
 cudaError_t launch_half_step_generic(int move_kind, const HalfStepArgs& a, cudaStream_t st);
 cudaError_t launch_logprob_generic(const ModelDev& m, const double* x, int64_t rows, int D, double* out,
                                    int* status, cudaStream_t st);

@@ -24,8 +24,10 @@ namespace eb {
 __global__ void __launch_bounds__(TABLE_THREADS) split_table_kernel(int32_t* __restrict__ order_base,
                                                                     const StepInfo* __restrict__ info,
                                                                     int64_t N, uint64_t seed,
-                                                                    uint64_t step0) {
+                                                                    uint64_t step0, int64_t w_lo, int64_t w_hi,
+                                                                    int2* __restrict__ ranges) {
   __shared__ int base[MAX_SPLITS];
+  __shared__ int own_lo[MAX_SPLITS], own_hi[MAX_SPLITS];  // set members below w_lo / w_hi
   __shared__ int chunk_tot[MAX_SPLITS];
   __shared__ int warp_off[MAX_SPLITS][32];
 
@@ -40,6 +42,8 @@ __global__ void __launch_bounds__(TABLE_THREADS) split_table_kernel(int32_t* __r
     int64_t s = 0;
     for (int j = 0; j < tid; ++j) s += (N - j + P - 1) / P;
     base[tid] = (int)s;
+    own_lo[tid] = 0;
+    own_hi[tid] = 0;
   }
   const FeistelKeys fk = feistel_keys(seed, step);
   const int h = feistel_half_bits((uint64_t)N);
@@ -55,6 +59,14 @@ __global__ void __launch_bounds__(TABLE_THREADS) split_table_kernel(int32_t* __r
       const unsigned b = __ballot_sync(0xffffffffu, sid == j);
       if (sid == j) my_prefix = __popc(b & ((1u << lane) - 1u));
       if (lane == 0) warp_off[j][warp] = __popc(b);
+      if (ranges != nullptr) {  // multi-GPU: how many members of set j precede this rank's row block / its end
+        const unsigned bl = __ballot_sync(0xffffffffu, sid == j && w < w_lo);
+        const unsigned bh = __ballot_sync(0xffffffffu, sid == j && w < w_hi);
+        if (lane == 0) {
+          if (bl) atomicAdd(&own_lo[j], __popc(bl));
+          if (bh) atomicAdd(&own_hi[j], __popc(bh));
+        }
+      }
     }
     __syncthreads();
     if (warp < P) {
@@ -74,11 +86,13 @@ __global__ void __launch_bounds__(TABLE_THREADS) split_table_kernel(int32_t* __r
     if (tid < P) base[tid] += chunk_tot[tid];
     __syncthreads();
   }
+  if (ranges != nullptr && tid < P) ranges[(size_t)blockIdx.x * MAX_SPLITS + tid] = make_int2(own_lo[tid], own_hi[tid]);
 }
 
 cudaError_t launch_split_tables(int32_t* order, const StepInfo* info_dev, int nsteps_chunk, int64_t N,
-                                uint64_t seed, uint64_t step0, cudaStream_t st) {
-  split_table_kernel<<<nsteps_chunk, TABLE_THREADS, 0, st>>>(order, info_dev, N, seed, step0);
+                                uint64_t seed, uint64_t step0, int64_t w_lo, int64_t w_hi, int2* ranges,
+                                cudaStream_t st) {
+  split_table_kernel<<<nsteps_chunk, TABLE_THREADS, 0, st>>>(order, info_dev, N, seed, step0, w_lo, w_hi, ranges);
   return cudaGetLastError();
 }
 
@@ -152,8 +166,10 @@ __global__ void __launch_bounds__(256) half_step_generic_kernel(const HalfStepAr
   const int gid = threadIdx.x / G, g = threadIdx.x % G;
   const int lane = threadIdx.x & 31;
   const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-  const int64_t i = (int64_t)a.i_lo + (int64_t)blockIdx.x * groups + gid;
-  if (i >= a.i_hi) return;  // whole groups leave together
+  const int i_lo = a.range ? a.range->x : a.i_lo;
+  const int i_hi = a.range ? a.range->y : a.i_hi;
+  const int64_t i = (int64_t)i_lo + (int64_t)blockIdx.x * groups + gid;
+  if (i >= i_hi) return;  // whole groups leave together
 
   double* q = smem + (size_t)gid * NROWS * D;
   double* xc = q + (size_t)(NROWS - 1) * D;  // centred row (dense model only)

@@ -36,7 +36,11 @@ class EnsembleSampler(object):
     """An ensemble MCMC sampler whose walker update runs on one B200.
 
     Args mirror ``ensemble.py:79-98``.  Extra keyword-only arguments: ``seed``
-    (Philox key; default derived from numpy's global state) and ``device``."""
+    (Philox key; default derived from numpy's global state), ``device``, and
+    ``pinned_results`` (the yielded / returned ``State`` arrays are views of two
+    page-locked buffers owned by the sampler and are overwritten by the next
+    step -- full-speed D2H for callers that consume each state before asking for
+    the next; default ``False`` = fresh arrays, as the reference returns)."""
 
     def __init__(
         self,
@@ -60,6 +64,7 @@ class EnsembleSampler(object):
         *,
         seed=None,
         device=0,
+        pinned_results=False,
     ):
         for name, val in (("a", a), ("postargs", postargs), ("threads", threads),
                           ("live_dangerously", live_dangerously), ("runtime_sortingfn", runtime_sortingfn)):
@@ -105,6 +110,9 @@ class EnsembleSampler(object):
                                    device=device)
         self._engine.set_model(log_prob_fn.kind, log_prob_fn.device_params(self.ndim))
         self._random = DeviceRandom(self._engine)
+        self._pinned = None
+        if pinned_results:
+            self._pinned = (_lib.pinned_empty((self.nwalkers, self.ndim)), _lib.pinned_empty((self.nwalkers,)))
 
         self.backend = Backend() if backend is None else backend
         if not self.backend.initialized:  # ensemble.py:137-141
@@ -175,7 +183,11 @@ class EnsembleSampler(object):
         if iterations is None and store:
             raise ValueError("'store' must be False when 'iterations' is None")
 
-        state = State(initial_state, copy=True)  # the caller's arrays are never touched
+        # ``State(initial_state, copy=True)`` in the reference (ensemble.py:312): here the
+        # upload to the device IS the copy -- the caller's arrays are only read, and
+        # the yielded State gets its own arrays from the first device read-back
+        state = State(initial_state)
+        state = State(state.coords, log_prob=state.log_prob, blobs=state.blobs, random_state=state.random_state)
         state_shape = np.shape(state.coords)
         if state_shape != (self.nwalkers, self.ndim):
             raise ValueError("incompatible input dimensions {0}".format(state_shape))
@@ -214,7 +226,10 @@ class EnsembleSampler(object):
         eng = self._engine
 
         def refresh():
-            state.coords, state.log_prob = eng.get_state()
+            if self._pinned is not None:
+                state.coords, state.log_prob = eng.get_state(*self._pinned)
+            else:
+                state.coords, state.log_prob = eng.get_state()
             state.random_state = self.random_state
 
         if _bulk and iterations is not None and (not store or (native_store and thin is None)):

@@ -99,6 +99,11 @@ class OracleSampler(object):
         self.naccepted = np.zeros(self.nwalkers, dtype=np.int64)
         self.rowwise = False  # per-row np.dot for snooker (bit-exact vs reference)
         self.taps = None  # last half-step's draws, for known-answer tests
+        # sharded emulation (tests of the multi-GPU scheme): only walkers in
+        # [owner_range) are updated by this instance, and ``exchange(coords,
+        # log_prob, accepted)`` is called after every split to merge the ranks
+        self.owner_range = None
+        self.exchange = None
 
     # -- ensemble.py:458-553 (only the parts that exist for a device model) --
     def compute_log_prob(self, coords):
@@ -207,10 +212,14 @@ class OracleSampler(object):
                 lnpdiff = factors + new_lp - self.log_prob[act]  # red_blue.py:99
                 acc = lnpdiff > np.log(uacc)  # red_blue.py:100
             self.taps.update(u_accept=uacc, active=act, q=q, new_lp=new_lp, factors=factors)
+            if self.owner_range is not None:
+                acc = acc & (act >= self.owner_range[0]) & (act < self.owner_range[1])
             won = act[acc]
             self.coords[won] = q[acc]  # move.py:33
             self.log_prob[won] = new_lp[acc]  # move.py:34
             accepted[won] = True
+            if self.exchange is not None:
+                self.exchange(self.coords, self.log_prob, accepted)
         return accepted
 
     def run(self, nsteps):
