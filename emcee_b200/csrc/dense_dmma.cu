@@ -7,17 +7,24 @@
 //   * A = L L^T is factored once on the host; lp = -0.5 |L^T (q - mu)|^2, i.e. a
 //     [walkers x D] x [D x D lower-triangular] product: only the blocks on or
 //     below the diagonal are multiplied (D(D+1) instead of 2 D^2 flops).
-//   * one warp owns a tile of 8 active walkers; mma.sync.m8n8k4.f64 (DMMA).  The
-//     A operand (the proposal rows q) lives in REGISTERS for the whole tile --
-//     lane (g, t) holds row g, physical columns {8j+2t, 8j+2t+1}, j < D/8, which
-//     it reads from HBM/L2 as 16-byte vectors; the contraction index is permuted
-//     accordingly when L is packed, which is free.  The same registers are the
-//     values written back if the proposal is accepted, so q is formed exactly
-//     once (bit-exact sub/mul/sub, no FMA contraction).
-//   * L (packed per 4x8 fragment, 256 B per DMMA, conflict-free LDS.64) is staged
-//     in shared memory once per CTA by cp.async; CTAs are persistent (one per SM)
-//     and tiles are dealt SM-major so every SM sub-partition gets the same count.
-//   * per-row |y|^2 is reduced over the 4 lanes of a row with two shuffles.
+//   * persistent CTAs, one per SM, warp specialised: 8 CONSUMER warps (two per SM
+//     sub-partition -- what the FP64 tensor pipe needs to stay saturated when its B
+//     operand streams from shared memory) and 8 PRODUCER warps, paired 1:1.
+//   * producer p: Philox draws, order[] lookups, old log-prob, the two logs of the
+//     accept test -> a small meta record in shared memory; 16 TMA bulk copies
+//     (cp.async.bulk, one whole 8*D-byte row each: the active walker's row and its
+//     partner's, possibly from a peer GPU over NVLink) into the pair's landing
+//     slot, completion counted on an mbarrier; then the proposal
+//     q = c - (c - s) z (bit-exact sub/mul/sub) written over the partner rows.
+//   * consumer c: loads q into REGISTERS (lane (g,t) holds row g, columns
+//     {8j+2t, 8j+2t+1}: the DMMA A fragments under a permutation of the contraction
+//     index that is folded into the packing of L, so rows move as 16-byte vectors),
+//     releases the slot (the producer refills it while the tile is on the tensor
+//     pipe), runs mma.sync.m8n8k4.f64 against the packed factor in shared memory,
+//     reduces |y|^2 over the 4 lanes of a row, applies the Metropolis test and
+//     writes accepted rows straight from those registers.  A consumer does almost
+//     nothing but DMMAs.
+//   * tiles (8 walkers) are dealt SM-major, so every sub-partition gets the same count.
 #include <math.h>
 
 #include "engine.cuh"
@@ -26,9 +33,9 @@ namespace eb {
 
 namespace {
 
-constexpr int DMMA_THREADS = 256;  // 8 warps, 2 per SM sub-partition (the tensor pipe needs no more)
-constexpr int DMMA_WARPS = DMMA_THREADS / 32;
-constexpr int NI = 4;  // column tiles in flight per warp (independent accumulator chains)
+constexpr int DMMA_CONSUMERS = 8;
+constexpr int DMMA_THREADS = 64 * DMMA_CONSUMERS;  // consumers are warps 0..7, producers 8..15
+constexpr int NI = 2;  // column tiles in flight per consumer (2*NI independent accumulator chains)
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -36,137 +43,214 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+// ---- mbarrier / TMA bulk copy primitives (PTX ISA 8.x, sm_90+) ----------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA, SASS UBLKCP); completion is counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 __host__ __device__ constexpr int packed_blocks(int KB) { return KB * (KB + 1); }  // 2 * KB(KB+1)/2
-// landing buffer of one warp: [s|c][8 rows][D + 8] doubles; the +8 (64 B) row skew
-// makes the 16-byte fragment reads of 8 consecutive lanes hit 32 distinct banks
+// landing slot of one pair: [s|c][8 rows][D + 8] doubles; the +8 (64 B) row skew
+// makes the 16-byte fragment accesses of 8 consecutive lanes hit 32 distinct banks
 __host__ __device__ constexpr int row_stride(int KB) { return 8 * KB + 8; }
-__host__ __device__ constexpr size_t dmma_smem_bytes(int KB) {
-  return ((size_t)packed_blocks(KB) * 32 + 8 * KB + (size_t)DMMA_WARPS * 2 * 8 * row_stride(KB)) * sizeof(double);
-}
 
-// what a lane must know about one tile before its rows can be fetched.  The two
-// walker ids are kept as the raw 32-bit words the index loads return: their first
-// consumer is pinned (below) behind the previous tile's tensor-pipe phase, so the
-// L2 latency of the order[] lookups is never waited for.
+// what the producer hands to the consumer besides q (one record per tile, two in flight)
 struct TileMeta {
-  int32_t w, wp;  // this lane's active walker and its partner (order[] entries)
-  double zz, u;   // stretch factor, accept uniform
-  bool valid;
+  double factor[8];  // (ndim - 1) log zz                              (stretch.py:31)
+  double log_u[8];   // log of the accept uniform                      (red_blue.py:100)
+  double lp_old[8];  // current log-prob of the active walker          (red_blue.py:99)
+  int32_t w[8];      // active walker id; < 0: padding row of a partial tile
 };
 
-// an opaque move: volatile asm statements keep their program order, so whatever
-// reads the result cannot be scheduled ahead of the DMMA block that precedes it
-__device__ __forceinline__ int32_t pin(int32_t x) {
-  int32_t y;
-  asm volatile("mov.b32 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
+template <int KB>
+struct SmemLayout {
+  static constexpr size_t L_doubles = (size_t)packed_blocks(KB) * 32;
+  static constexpr size_t mu_doubles = 8 * KB;
+  static constexpr size_t slot_doubles = 2 * 8 * row_stride(KB);
+  static constexpr size_t off_mu = L_doubles;
+  static constexpr size_t off_slots = off_mu + mu_doubles;
+  static constexpr size_t off_meta = off_slots + DMMA_CONSUMERS * slot_doubles;  // in doubles
+  static constexpr size_t meta_bytes = sizeof(TileMeta) * 2 * DMMA_CONSUMERS;
+  static constexpr size_t off_bars_bytes = off_meta * sizeof(double) + meta_bytes;
+  static constexpr size_t total_bytes = off_bars_bytes + (1 + 3 * DMMA_CONSUMERS) * sizeof(uint64_t);
+};
 
 template <int KB, bool HAS_MEAN>
 __global__ void __launch_bounds__(DMMA_THREADS, 1) half_step_dense_dmma_kernel(const HalfStepArgs a) {
   constexpr int D = 8 * KB;
   constexpr int RS = row_stride(KB);
-  extern __shared__ double smem[];
-  double* sL = smem;                            // packed_blocks(KB) * 32 doubles
-  double* sMu = sL + packed_blocks(KB) * 32;    // D doubles
-  double* sRows = sMu + D;                      // DMMA_WARPS * 2 * 8 * RS doubles
+  using SL = SmemLayout<KB>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sL = reinterpret_cast<double*>(smem_raw);
+  double* sMu = sL + SL::off_mu;
+  double* sSlots = sL + SL::off_slots;
+  TileMeta* sMeta = reinterpret_cast<TileMeta*>(sL + SL::off_meta);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + SL::off_bars_bytes);
+  uint64_t* barL = bars;                                  // packed factor landed
+  uint64_t* barFull = bars + 1;                           // [pair] TMA: rows of a tile landed
+  uint64_t* barReady = bars + 1 + DMMA_CONSUMERS;         // [pair] producer: proposal written
+  uint64_t* barFree = bars + 1 + 2 * DMMA_CONSUMERS;      // [pair] consumer: slot may be refilled
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_producer = warp >= DMMA_CONSUMERS;
+  const int pair = is_producer ? warp - DMMA_CONSUMERS : warp;
   const int g = lane >> 2, t = lane & 3;
-  double* myS = sRows + (size_t)warp * 2 * 8 * RS + (size_t)g * RS + 2 * t;  // this lane's chunks of row g
-  double* myC = myS + 8 * RS;
 
-  // ---- stage the packed factor (and the mean) in shared memory, asynchronously
-  {
-    const double* src = a.model.chol;
-    constexpr int n16 = packed_blocks(KB) * 32 / 2;
-    for (int k = tid; k < n16; k += DMMA_THREADS) cp_async16(sL + 2 * k, src + 2 * k);
-    if (HAS_MEAN)
-      for (int k = tid; k < D; k += DMMA_THREADS) sMu[k] = a.model.params[k];
+  if (tid == 0) {
+    mbar_init(barL, 1);
+    for (int c = 0; c < DMMA_CONSUMERS; ++c) {
+      mbar_init(barFull + c, 1);
+      mbar_init(barReady + c, 1);
+      mbar_init(barFree + c, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (HAS_MEAN)
+    for (int k = tid; k < D; k += DMMA_THREADS) sMu[k] = a.model.params[k];
+  __syncthreads();
+  if (tid == 0) {  // one bulk copy brings the whole packed factor
+    constexpr unsigned bytes = (unsigned)(SL::L_doubles * sizeof(double));
+    mbar_arrive_expect_tx(barL, bytes);
+    bulk_g2s(sL, a.model.chol, bytes, barL);
   }
 
   const int i_lo = a.range ? a.range->x : a.i_lo;
   const int i_hi = a.range ? a.range->y : a.i_hi;
   const int64_t count = (int64_t)i_hi - i_lo;
   const int64_t ntiles = (count + 7) >> 3;
-  const int64_t Nc = a.N - a.a_count;
-  const double dm1 = (double)a.D - 1.0;
-  const int64_t tstride = (int64_t)gridDim.x * DMMA_WARPS;
+  const int64_t tstride = (int64_t)gridDim.x * DMMA_CONSUMERS;
+  const int64_t tile0 = (int64_t)blockIdx.x + (int64_t)gridDim.x * pair;  // SM-major deal
+  double* slot = sSlots + (size_t)pair * SL::slot_doubles;
+  double* myS = slot + (size_t)g * RS + 2 * t;  // this lane's 16-byte chunks of row g
+  double* myC = myS + 8 * RS;                   // partner row, later the proposal
+  TileMeta* meta = sMeta + 2 * pair;
 
-  // draws + index lookups of one tile (stretch.py:30-32, red_blue.py:82-87,100)
-  auto prep = [&](int64_t tile) -> TileMeta {
-    TileMeta m;
-    int64_t i = (int64_t)i_lo + tile * 8 + g;
-    m.valid = i < i_hi;
-    if (!m.valid) i = (int64_t)i_hi - 1;
-    const u32x4 A = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_PROP_A, (uint32_t)i);
-    const double tt = __dadd_rn(__dmul_rn(__dsub_rn(a.p0, 1.0), u53(A.x, A.y)), 1.0);
-    m.zz = __ddiv_rn(__dmul_rn(tt, tt), a.p0);
-    const int64_t r = (int64_t)bounded64(A.z, A.w, (uint64_t)Nc);
-    m.w = __ldg(a.order + a.a_start + i);
-    m.wp = __ldg(a.order + (r < a.a_start ? r : r + a.a_count));
-    const u32x4 U = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_ACCEPT, (uint32_t)i);
-    m.u = u53(U.x, U.y);
-    return m;
-  };
-  // asynchronous gather of this lane's 16-byte chunks of both rows into the landing buffer
-  auto fetch = [&](int64_t w, int64_t wp) {
-    const double* s_row = a.coords + (size_t)w * D + 2 * t;
-    const double* c_row =
-        (a.peer_coords != nullptr ? a.peer_coords[wp / a.rows_per_rank] : a.coords) + (size_t)wp * D + 2 * t;
+  if (is_producer) {
+    // ================= producer: draws, lookups, TMA row gather, proposal =================
+    const int64_t Nc = a.N - a.a_count;
+    const double dm1 = (double)a.D - 1.0;
+    const int row = lane & 7;
+    // per-row quantities of one tile (lanes 0..7 own rows 0..7; the other lanes mirror them)
+    struct Prep {
+      int32_t w, wp;
+      double zz, factor, log_u, lp_old;
+      bool valid;
+    };
+    auto prep = [&](int64_t tile) -> Prep {
+      Prep p;
+      int64_t i = (int64_t)i_lo + tile * 8 + row;
+      p.valid = i < i_hi;
+      if (!p.valid) i = (int64_t)i_hi - 1;
+      const u32x4 A = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_PROP_A, (uint32_t)i);
+      const double tt = __dadd_rn(__dmul_rn(__dsub_rn(a.p0, 1.0), u53(A.x, A.y)), 1.0);  // stretch.py:30
+      p.zz = __ddiv_rn(__dmul_rn(tt, tt), a.p0);
+      const int64_t r = (int64_t)bounded64(A.z, A.w, (uint64_t)Nc);  // stretch.py:32
+      p.w = __ldg(a.order + a.a_start + i);
+      p.wp = __ldg(a.order + (r < a.a_start ? r : r + a.a_count));
+      const u32x4 U = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_ACCEPT, (uint32_t)i);
+      p.log_u = log(u53(U.x, U.y));
+      p.factor = __dmul_rn(dm1, log(p.zz));  // stretch.py:31
+      p.lp_old = a.logp[p.w];                // looked up a whole tile ahead of its use
+      return p;
+    };
+    // publish the meta record and launch the 16 row copies of one tile into the landing slot
+    auto issue = [&](const Prep& p, int par) {
+      TileMeta* m = meta + par;
+      if (lane < 8) {
+        m->factor[row] = p.factor;
+        m->log_u[row] = p.log_u;
+        m->lp_old[row] = p.lp_old;
+        m->w[row] = p.valid ? p.w : -1;
+      }
+      if (lane == 0) mbar_arrive_expect_tx(barFull + pair, 16u * D * (unsigned)sizeof(double));
+      __syncwarp();
+      if (lane < 16) {
+        const bool partner = lane >= 8;
+        const int64_t wr = partner ? (int64_t)p.wp : (int64_t)p.w;
+        const double* base = (partner && a.peer_coords != nullptr) ? a.peer_coords[wr / a.rows_per_rank] : a.coords;
+        bulk_g2s(slot + (size_t)(partner ? 8 : 0) * RS + (size_t)row * RS, base + (size_t)wr * D,
+                 (unsigned)(D * sizeof(double)), barFull + pair);
+      }
+    };
+    if (tile0 < ntiles) {
+      Prep cur = prep(tile0);
+      issue(cur, 0);
+      Prep nxt = cur;
+      if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride);
+      unsigned k = 0;
+      for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++k) {
+        // ---- rows of tile k have landed: form the proposal over the partner rows
+        const double zz = __shfl_sync(0xffffffffu, cur.zz, g);
+        mbar_wait(barFull + pair, k & 1u);
 #pragma unroll
-    for (int j = 0; j < KB; ++j) {
-      cp_async16(myS + 8 * j, s_row + 8 * j);
-      cp_async16(myC + 8 * j, c_row + 8 * j);
+        for (int j = 0; j < KB; ++j) {
+          const double2 s2 = *reinterpret_cast<const double2*>(myS + 8 * j);
+          const double2 c2 = *reinterpret_cast<const double2*>(myC + 8 * j);
+          // stretch.py:33  q = c - (c - s) * zz, each op rounded once (no FMA contraction)
+          double2 q2;
+          q2.x = __dsub_rn(c2.x, __dmul_rn(__dsub_rn(c2.x, s2.x), zz));
+          q2.y = __dsub_rn(c2.y, __dmul_rn(__dsub_rn(c2.y, s2.y), zz));
+          *reinterpret_cast<double2*>(myC + 8 * j) = q2;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(barReady + pair);
+        // ---- as soon as the consumer has the proposal in registers, refill the slot
+        if (tile + tstride < ntiles) {
+          cur = nxt;
+          mbar_wait(barFree + pair, k & 1u);
+          issue(cur, (int)((k + 1) & 1u));
+          if (tile + 2 * tstride < ntiles) nxt = prep(tile + 2 * tstride);
+        }
+      }
     }
-  };
-
-  // tiles dealt SM-major: CTA b takes b, b+G, b+2G, ...; its warps take them round-robin.
-  // Software pipeline per warp: rows of tile k+1 stream into shared memory (LDGSTS, no
-  // registers) and the indices of tile k+2 are looked up while tile k is on the tensor pipe.
-  int64_t tile = (int64_t)blockIdx.x + (int64_t)gridDim.x * warp;
-  TileMeta cur{}, nxt{};
-  if (tile < ntiles) {
-    cur = prep(tile);
-    fetch(cur.w, cur.wp);
-    if (tile + tstride < ntiles) nxt = prep(tile + tstride);
+    return;
   }
-  cp_async_wait_all();  // the factor chunks this thread copied (and tile 0's rows)
-  __syncthreads();      // ... and everybody else's
 
-  for (; tile < ntiles; tile += tstride) {
-    cp_async_wait_all();
-    // ---- form the proposal in registers (stretch.py:33, each op rounded once)
+  // ================================ consumer: DMMA, accept, update ================================
+  mbar_wait(barL, 0);
+  unsigned k = 0;
+  for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++k) {
+    const TileMeta* m = meta + (k & 1u);
+    mbar_wait(barReady + pair, k & 1u);
     double q[2 * KB];
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
-      const double2 s2 = *reinterpret_cast<const double2*>(myS + 8 * j);
-      const double2 c2 = *reinterpret_cast<const double2*>(myC + 8 * j);
-      q[2 * j + 0] = __dsub_rn(c2.x, __dmul_rn(__dsub_rn(c2.x, s2.x), cur.zz));
-      q[2 * j + 1] = __dsub_rn(c2.y, __dmul_rn(__dsub_rn(c2.y, s2.y), cur.zz));
+      const double2 q2 = *reinterpret_cast<const double2*>(myC + 8 * j);
+      q[2 * j + 0] = q2.x;
+      q[2 * j + 1] = q2.y;
     }
-    const int64_t w_cur = cur.w;
-    const double lp_old = a.logp[w_cur];
-    // ---- keep the pipeline full: rows of the next tile, indices of the one after
-    const bool has_next = tile + tstride < ntiles;
-    TileMeta ready = nxt;
-    if (has_next) {
-      ready.w = pin(ready.w);  // looked up one tensor-pipe phase ago
-      ready.wp = pin(ready.wp);
-      fetch(ready.w, ready.wp);
-      if (tile + 2 * tstride < ntiles) nxt = prep(tile + 2 * tstride);
-    }
+    const int32_t w = m->w[g];
+    const double factor = m->factor[g], log_u = m->log_u[g], lp_old = m->lp_old[g];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(barFree + pair);  // slot and meta may be refilled while this tile computes
 
-    // ---- y = L^T (q - mu) block by block on the tensor pipe; rs = sum_n y_n^2.
-    // A dependent DMMA chain issues only every ~64 cycles, the pipe takes one every
-    // 16 per sub-partition: NI column tiles x 2 k-halves = 2*NI independent
-    // accumulator chains per warp keep it fed with 2 warps per sub-partition.
+    // ---- y = L^T (q - mu) block by block on the tensor pipe; rs = sum_n y_n^2
     double rs = 0.0;
     const double* bptr = sL + lane;
 #pragma unroll
@@ -207,9 +291,9 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1) half_step_dense_dmma_kernel(c
     if (!isfinite(lp_new)) {
       bool any_inf = false, any_nan = false;
 #pragma unroll
-      for (int k = 0; k < 2 * KB; ++k) {
-        any_inf |= isinf(q[k]);
-        any_nan |= isnan(q[k]);
+      for (int kk = 0; kk < 2 * KB; ++kk) {
+        any_inf |= isinf(q[kk]);
+        any_nan |= isnan(q[kk]);
       }
       if (any_inf) atomicOr(a.status, FLAG_INF_PARAM);
       if (any_nan) atomicOr(a.status, FLAG_NAN_PARAM);
@@ -217,28 +301,26 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1) half_step_dense_dmma_kernel(c
     }
 
     // ---- Metropolis accept + in-place update (red_blue.py:96-104, move.py:29-34)
-    const double factor = __dmul_rn(dm1, log(cur.zz));  // stretch.py:31
     const double lnpdiff = __dsub_rn(__dadd_rn(factor, lp_new), lp_old);
-    const bool acc = cur.valid && (lnpdiff > log(cur.u));
+    const bool acc = (w >= 0) && (lnpdiff > log_u);
     if (acc) {
-      double* dst = a.coords + (size_t)w_cur * D + 2 * t;
+      double* dst = a.coords + (size_t)w * D + 2 * t;
 #pragma unroll
       for (int j = 0; j < KB; ++j) *reinterpret_cast<double2*>(dst + 8 * j) = make_double2(q[2 * j], q[2 * j + 1]);
     }
-    if (cur.valid && t == 0) {
+    if (w >= 0 && t == 0) {
       if (acc) {
-        a.logp[w_cur] = lp_new;
-        atomicAdd(a.nacc + w_cur, 1ull);  // RED: fire and forget, no load to wait for
+        a.logp[w] = lp_new;
+        atomicAdd(a.nacc + w, 1ull);  // RED: fire and forget
       }
-      a.accepted[w_cur] = acc ? 1 : 0;
+      a.accepted[w] = acc ? 1 : 0;
     }
-    cur = ready;
   }
 }
 
 template <int KB>
 cudaError_t launch_t(const HalfStepArgs& a, int sm_count, cudaStream_t st) {
-  const size_t smem = dmma_smem_bytes(KB);
+  const size_t smem = SmemLayout<KB>::total_bytes;
   const bool has_mean = a.model.s0 != 0.0;  // set by eb_model_set when mu != 0
   auto kern = has_mean ? half_step_dense_dmma_kernel<KB, true> : half_step_dense_dmma_kernel<KB, false>;
   if (smem > 48 * 1024) {
