@@ -248,6 +248,8 @@ def run_b200(args, dist):
 
     ebdist.attach(eng, dist, args.comm)
     eng.set_option("l2_flush", 1 if args.l2_flush else 0)
+    if args.dmma_group > 0:
+        eng.set_option("dmma_group", args.dmma_group)
     sched = sampler._schedule()
 
     # ---- device-resident throughput (`value`) ------------------------------
@@ -350,6 +352,7 @@ def main():
     ap.add_argument("--comm", default="allgather", choices=["allgather", "p2p"])
     ap.add_argument("--no-l2-flush", dest="l2_flush", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dmma-group", type=int, default=0, help="half-steps per persistent dense_dmma launch (0: library default)")
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--cpu-nwalkers", type=int, default=65536)
     args = ap.parse_args()

@@ -80,6 +80,7 @@ _SIGNATURES = {
         [C.c_void_p, C.POINTER(C.c_int64), _dp, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     ),
     "eb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "eb_debug_timeline": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_size_t, C.POINTER(C.c_size_t)]),
     "eb_last_kernel_name": (C.c_char_p, [C.c_void_p]),
     "eb_microbench": (C.c_int, [C.c_int, C.c_int, _dp]),
     "eb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -312,6 +313,13 @@ class Engine(object):
         )
         k = int(cnt.value)
         return dict(partners=partners[:, :k], scalar=scalar[:k], u_accept=u[:k], active=active[:k])
+
+    def debug_timeline(self):
+        """[SM, consumer, tile, event] cycle stamps of the last dense_dmma half-step."""
+        buf = np.zeros(1 << 20, dtype=np.int64)
+        n = C.c_size_t()
+        self._check(lib().eb_debug_timeline(self._h, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(n)))
+        return buf[: n.value].reshape(-1, 8, 8, 6)
 
     # -- multi-GPU ---------------------------------------------------------------
     @staticmethod

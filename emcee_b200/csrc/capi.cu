@@ -38,6 +38,10 @@ struct eb_ctx {
   size_t table_cap = 0;
   StepInfo* info_dev = nullptr;
   StepInfo* info_host = nullptr;  // pinned
+  HalfDesc* descs_dev = nullptr;  // [table_cap * MAX_SPLITS] half-step descriptors of a chunk (dense_dmma)
+  HalfDesc* descs_host = nullptr;  // pinned
+  unsigned long long* gbar = nullptr;  // grid-barrier counter of the persistent dense_dmma kernel
+  unsigned long long gbar_count = 0;   // arrivals issued so far
 
   double* scratch_x = nullptr;
   double* scratch_lp = nullptr;
@@ -54,6 +58,7 @@ struct eb_ctx {
   double* tap_u = nullptr;
   int64_t* tap_active = nullptr;
   int64_t tap_count = 0;
+  long long* timeline = nullptr;  // dense_dmma instrumentation buffer (option "dmma_timeline")
 
   // optional L2 flush between steps (benchmark hygiene): per-step event pairs
   bool l2_flush = false;
@@ -65,6 +70,7 @@ struct eb_ctx {
   uint64_t last_launches = 0;
   const char* last_kernel = "none";
   bool allow_dmma = true;
+  int dmma_group = 1;  // half-steps per persistent dense_dmma launch (1: a launch per half-step)
 
   Comm comm;  // multi-GPU (comm.h)
 
@@ -186,6 +192,10 @@ int eb_create(int device, int64_t nwalkers, int64_t ndim, uint64_t seed, eb_ctx*
   CC(cudaMalloc(&c->order, cap * (size_t)nwalkers * sizeof(int32_t)));
   CC(cudaMalloc(&c->info_dev, cap * sizeof(StepInfo)));
   CC(cudaMallocHost(&c->info_host, cap * sizeof(StepInfo)));
+  CC(cudaMalloc(&c->descs_dev, cap * MAX_SPLITS * sizeof(HalfDesc)));
+  CC(cudaMallocHost(&c->descs_host, cap * MAX_SPLITS * sizeof(HalfDesc)));
+  CC(cudaMalloc(&c->gbar, sizeof(unsigned long long)));
+  CC(cudaMemsetAsync(c->gbar, 0, sizeof(unsigned long long), c->st));
   CC(cudaStreamSynchronize(c->st));
 #undef CC
   *out = c;
@@ -208,6 +218,9 @@ int eb_destroy(eb_ctx* c) {
   cudaFree(c->order);
   cudaFree(c->info_dev);
   cudaFreeHost(c->info_host);
+  cudaFree(c->descs_dev);
+  cudaFreeHost(c->descs_host);
+  cudaFree(c->gbar);
   cudaFree(c->scratch_x);
   cudaFree(c->scratch_lp);
   for (int k = 0; k < 2; ++k) {
@@ -217,6 +230,7 @@ int eb_destroy(eb_ctx* c) {
   }
   cudaFree(c->flush_buf);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  cudaFree(c->timeline);
   cudaFree(c->tap_partners);
   cudaFree(c->tap_scalar);
   cudaFree(c->tap_u);
@@ -438,29 +452,21 @@ size_t choose_move(const eb_ctx* c, const Schedule& s, uint64_t step) {
   return idx;
 }
 
-// launch the P half-steps of one step
-int launch_step(eb_ctx* c, const eb_move& mv, uint64_t step, const int32_t* order, size_t step_in_chunk,
-                uint64_t& launches) {
-  const int P = mv.nsplits;
-  const int64_t N = c->N;
-  if (N < 2 * (int64_t)c->D && !mv.live_dangerously)  // red_blue.py:64-70
-    FAIL(c, EB_ERR_FEW_WALKERS,
-         "It is unadvisable to use a red-blue move with fewer walkers than twice the number of dimensions.");
-  int start[MAX_SPLITS + 1];
+void split_starts(int64_t N, int P, int* start) {
   start[0] = 0;
   for (int j = 0; j < P; ++j) start[j + 1] = start[j] + (int)((N - j + P - 1) / P);
+}
 
-  HalfStepArgs a{};
+void fill_base_args(eb_ctx* c, const eb_move& mv, HalfStepArgs& a) {
+  a = HalfStepArgs{};
   a.coords = c->coords;
   a.logp = c->logp;
   a.accepted = c->accepted;
   a.nacc = c->nacc;
   a.status = c->status_dev;
-  a.order = order;
-  a.N = N;
+  a.N = c->N;
   a.D = c->D;
   a.seed = c->seed;
-  a.step = step;
   a.model = c->model;
   if (c->debug) {
     a.tap_partners = c->tap_partners;
@@ -479,9 +485,34 @@ int launch_step(eb_ctx* c, const eb_move& mv, uint64_t step, const int32_t* orde
     default:
       a.p0 = mv.p0;  // gammas
   }
+  a.timeline = c->timeline;
   comm_fill_args(c->comm, a);
-  const bool dmma = c->allow_dmma && mv.kind == EB_MOVE_STRETCH && c->model.kind == EB_MODEL_GAUSS_DENSE &&
-                    c->model.chol != nullptr && !c->debug;
+}
+
+bool dmma_eligible(const eb_ctx* c, const eb_move& mv) {
+  return c->allow_dmma && mv.kind == EB_MOVE_STRETCH && c->model.kind == EB_MODEL_GAUSS_DENSE &&
+         c->model.chol != nullptr && !c->debug;
+}
+
+int check_walker_count(eb_ctx* c, const eb_move& mv) {
+  if (c->N < 2 * (int64_t)c->D && !mv.live_dangerously)  // red_blue.py:64-70
+    FAIL(c, EB_ERR_FEW_WALKERS,
+         "It is unadvisable to use a red-blue move with fewer walkers than twice the number of dimensions.");
+  return EB_OK;
+}
+
+// launch the P half-steps of one step with the generic kernels (one launch per split)
+int launch_step_generic(eb_ctx* c, const eb_move& mv, uint64_t step, const int32_t* order, size_t step_in_chunk,
+                        uint64_t& launches) {
+  const int P = mv.nsplits;
+  int rc = check_walker_count(c, mv);
+  if (rc) return rc;
+  int start[MAX_SPLITS + 1];
+  split_starts(c->N, P, start);
+  HalfStepArgs a;
+  fill_base_args(c, mv, a);
+  a.order = order;
+  a.step = step;
   for (int split = 0; split < P; ++split) {
     a.split = split;
     a.a_start = start[split];
@@ -494,26 +525,45 @@ int launch_step(eb_ctx* c, const eb_move& mv, uint64_t step, const int32_t* orde
       ++k;
     }
     comm_active_range(c->comm, a, step_in_chunk);  // i_lo / i_hi for this rank
-    int rc;
-    if (dmma) {
-      CK(c, launch_half_step_dense_dmma(a, c->sm_count, c->st));
-      c->last_kernel = "dense_dmma";
-    } else {
-      CK(c, launch_half_step_generic(mv.kind, a, c->st));
-      c->last_kernel = "generic";
-    }
+    CK(c, launch_half_step_generic(mv.kind, a, c->st));
+    c->last_kernel = "generic";
     ++launches;
     c->tap_count = a.a_count;
-    rc = comm_after_split(c->comm, c->st, c->status_dev, launches);  // exchange the updated rows
-    if (rc) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+    if (comm_after_split(c->comm, c->st, c->status_dev, launches)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
   }
   return EB_OK;
 }
 
-// run nsteps steps; `after_step(k)` is called (with work for step k enqueued)
-// when non-null and may enqueue copies on the stream
+// a run of consecutive half-steps handed to ONE persistent dense_dmma launch
+struct DmmaGroup {
+  size_t first = 0;  // index into the chunk's HalfDesc array
+  int nhalf = 0;
+  int max_count = 0;
+};
+
+int flush_dmma(eb_ctx* c, const eb_move& mv, DmmaGroup& grp, uint64_t& launches) {
+  if (grp.nhalf == 0) return EB_OK;
+  HalfStepArgs a;
+  fill_base_args(c, mv, a);
+  a.order = c->order;  // chunk base; HalfDesc::order_step selects the table
+  a.range = c->comm.nranks > 1 ? c->comm.ranges : nullptr;
+  int bound = grp.max_count;
+  if (c->comm.nranks > 1 && c->comm.rows_per_rank < bound) bound = (int)c->comm.rows_per_rank;
+  int grid = 0;
+  CK(c, launch_dense_dmma(a, c->descs_dev + grp.first, grp.nhalf, bound, c->gbar, c->gbar_count, c->sm_count, &grid,
+                          c->st));
+  c->gbar_count += (unsigned long long)(grp.nhalf - 1) * (unsigned long long)grid;
+  c->last_kernel = "dense_dmma";
+  ++launches;
+  grp = DmmaGroup{};
+  return EB_OK;
+}
+
+// run nsteps steps.  `after_step(k)` is called with the work of step k enqueued and may
+// enqueue copies on the stream; `sync_every` > 0 tells how often it actually does (every
+// sync_every-th step), so that steps in between can share one persistent launch.
 template <class F>
-int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, F&& after_step) {
+int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every, F&& after_step) {
   uint64_t launches = 0;
   const bool perstep = c->l2_flush;  // flush L2 before every step, time each step on its own
   if (perstep) {
@@ -527,33 +577,91 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, F&& after_step) {
   }
   CK(c, cudaEventRecord(c->ev0, c->st));
   if (comm_begin(c->comm, c->st, c->status_dev, launches)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+  const bool multi = c->comm.nranks > 1;
   std::vector<size_t> pick;
   uint64_t done = 0;
   while (done < nsteps) {
     const size_t chunk = (size_t)std::min<uint64_t>(nsteps - done, c->table_cap);
     pick.resize(chunk);
-    CK(c, cudaStreamSynchronize(c->st));  // info_host is reused per chunk
+    CK(c, cudaStreamSynchronize(c->st));  // info_host / descs_host are reused per chunk
+    size_t ndesc = 0;
     for (size_t k = 0; k < chunk; ++k) {
       pick[k] = choose_move(c, s, c->step + k);
-      c->info_host[k].nsplits = s.moves[pick[k]].nsplits;
-      c->info_host[k].randomize = s.moves[pick[k]].randomize_split;
+      const eb_move& mv = s.moves[pick[k]];
+      c->info_host[k].nsplits = mv.nsplits;
+      c->info_host[k].randomize = mv.randomize_split;
+      if (dmma_eligible(c, mv)) {
+        int start[MAX_SPLITS + 1];
+        split_starts(c->N, mv.nsplits, start);
+        for (int split = 0; split < mv.nsplits; ++split) {
+          HalfDesc& d = c->descs_host[ndesc++];
+          d.step = c->step + k;
+          d.order_step = (int32_t)k;
+          d.split = split;
+          d.a_start = start[split];
+          d.a_count = start[split + 1] - start[split];
+        }
+      }
     }
+    DmmaGroup grp;
+    size_t desc_cursor = 0;
+    const eb_move* grp_move = nullptr;
     for (size_t k = 0; k < chunk; ++k) {
+      const eb_move& mv = s.moves[pick[k]];
       if (perstep) {
         CK(c, cudaMemsetAsync(c->flush_buf, (int)(k & 0xff), c->flush_bytes, c->st));
         CK(c, cudaEventRecord(c->ev_pool[2 * (done + k)], c->st));
       }
       if (k == 0) {
-        // split tables of the whole chunk (charged to the chunk's first step)
+        // split tables (and dense_dmma descriptors) of the whole chunk, charged to its first step
         CK(c, cudaMemcpyAsync(c->info_dev, c->info_host, chunk * sizeof(StepInfo), cudaMemcpyHostToDevice, c->st));
+        if (ndesc)
+          CK(c, cudaMemcpyAsync(c->descs_dev, c->descs_host, ndesc * sizeof(HalfDesc), cudaMemcpyHostToDevice, c->st));
         const Comm& cm = c->comm;
         CK(c, launch_split_tables(c->order, c->info_dev, (int)chunk, c->N, c->seed, c->step,
                                   cm.rows_per_rank * cm.rank, cm.rows_per_rank * (cm.rank + 1),
                                   cm.nranks > 1 ? cm.ranges : nullptr, c->st));
         ++launches;
       }
-      int rc = launch_step(c, s.moves[pick[k]], c->step, c->order + k * (size_t)c->N, k, launches);
-      if (rc) return rc;
+      int rc;
+      if (dmma_eligible(c, mv)) {
+        rc = check_walker_count(c, mv);
+        if (rc) return rc;
+        if (grp_move && grp_move != &mv) {  // a different move object: its parameters differ
+          rc = flush_dmma(c, *grp_move, grp, launches);
+          if (rc) return rc;
+        }
+        grp_move = &mv;
+        for (int split = 0; split < mv.nsplits; ++split) {
+          const HalfDesc& d = c->descs_host[desc_cursor];
+          if (grp.nhalf == 0) grp.first = desc_cursor;
+          grp.nhalf += 1;
+          grp.max_count = std::max(grp.max_count, (int)d.a_count);
+          ++desc_cursor;
+          if (!multi && grp.nhalf >= c->dmma_group && split + 1 < mv.nsplits) {
+            rc = flush_dmma(c, mv, grp, launches);
+            if (rc) return rc;
+          }
+          if (multi) {  // ranks exchange rows after every split: one half-step per launch
+            rc = flush_dmma(c, mv, grp, launches);
+            if (rc) return rc;
+            if (comm_after_split(c->comm, c->st, c->status_dev, launches))
+              FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+          }
+        }
+        const bool host_event = perstep || (sync_every > 0 && (done + k + 1) % sync_every == 0);
+        if (host_event || k + 1 == chunk || grp.nhalf >= c->dmma_group) {
+          rc = flush_dmma(c, mv, grp, launches);
+          if (rc) return rc;
+        }
+      } else {
+        if (grp_move) {
+          rc = flush_dmma(c, *grp_move, grp, launches);
+          if (rc) return rc;
+        }
+        rc = launch_step_generic(c, mv, c->step, c->order + k * (size_t)c->N, k, launches);
+        if (rc) return rc;
+      }
       c->step += 1;
       if (perstep) CK(c, cudaEventRecord(c->ev_pool[2 * (done + k) + 1], c->st));
       rc = after_step(done + k);
@@ -603,7 +711,7 @@ int eb_step(eb_ctx* c, const eb_move* moves, size_t nmoves, uint64_t nsteps, uin
   rc = build_schedule(c, moves, nmoves, s);
   if (rc) return rc;
   if (nsteps > 0) {
-    rc = run_steps(c, s, nsteps, [](uint64_t) { return EB_OK; });
+    rc = run_steps(c, s, nsteps, 0, [](uint64_t) { return EB_OK; });
     if (rc) return rc;
   }
   if (accepted_last) {
@@ -647,7 +755,7 @@ int eb_step_store(eb_ctx* c, const eb_move* moves, size_t nmoves, uint64_t nstep
     pending[slot] = -1;
     return EB_OK;
   };
-  rc = run_steps(c, s, nsteps, [&](uint64_t k) -> int {
+  rc = run_steps(c, s, nsteps, thin_by, [&](uint64_t k) -> int {
     if ((k + 1) % thin_by != 0) return EB_OK;  // ensemble.py:416
     const int slot = (int)(stored & 1);
     int r = drain(slot);
@@ -706,8 +814,25 @@ int eb_set_option(eb_ctx* c, const char* name, int64_t value) {
     c->debug = value != 0;
     return EB_OK;
   }
+  if (!strcmp(name, "dmma_timeline")) {
+    CK(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)c->sm_count * 8 * TL_TILES * TL_EVENTS;
+    if (value && !c->timeline) {
+      CK(c, cudaMalloc(&c->timeline, n * sizeof(long long)));
+      CK(c, cudaMemset(c->timeline, 0, n * sizeof(long long)));
+    } else if (!value && c->timeline) {
+      cudaFree(c->timeline);
+      c->timeline = nullptr;
+    }
+    return EB_OK;
+  }
   if (!strcmp(name, "l2_flush")) {
     c->l2_flush = value != 0;
+    return EB_OK;
+  }
+  if (!strcmp(name, "dmma_group")) {
+    if (value < 1) FAIL(c, EB_ERR_INVALID, "dmma_group must be >= 1");
+    c->dmma_group = (int)std::min<int64_t>(value, 1 << 20);
     return EB_OK;
   }
   if (!strcmp(name, "dense_dmma")) {
@@ -715,6 +840,17 @@ int eb_set_option(eb_ctx* c, const char* name, int64_t value) {
     return EB_OK;
   }
   FAIL(c, EB_ERR_INVALID, "eb_set_option: unknown option '%s'", name);
+}
+
+int eb_debug_timeline(eb_ctx* c, int64_t* out, size_t capacity, size_t* written) {
+  if (!c || !out) return EB_ERR_INVALID;
+  if (!c->timeline) FAIL(c, EB_ERR_STATE, "eb_debug_timeline: enable with eb_set_option(\"dmma_timeline\", 1)");
+  CK(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)c->sm_count * 8 * TL_TILES * TL_EVENTS;
+  if (capacity < n) FAIL(c, EB_ERR_INVALID, "eb_debug_timeline: need room for %zu values", n);
+  CK(c, cudaMemcpy(out, c->timeline, n * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (written) *written = n;
+  return EB_OK;
 }
 
 int eb_debug_taps(eb_ctx* c, int64_t* partners, double* scalar, double* u_accept, int64_t* active,

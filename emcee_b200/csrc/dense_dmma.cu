@@ -25,6 +25,10 @@
 //     writes accepted rows straight from those registers.  A consumer does almost
 //     nothing but DMMAs.
 //   * tiles (8 walkers) are dealt SM-major, so every sub-partition gets the same count.
+//   * one cooperative launch runs MANY half-steps (all splits of all steps up to the
+//     next host-visible event): between half-steps the CTAs meet at a grid barrier on
+//     a global counter instead of paying a kernel boundary (launch gap, re-staging of
+//     the 70 KB factor, pipeline refill from cold).
 #include <math.h>
 
 #include "engine.cuh"
@@ -54,18 +58,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// bounded wait: a lost partner traps the kernel (an error the host reports) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) __trap();  // ~4 s
+  }
 }
 // global -> shared bulk copy (TMA, SASS UBLKCP); completion is counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
@@ -101,8 +113,31 @@ struct SmemLayout {
   static constexpr size_t total_bytes = off_bars_bytes + (1 + 3 * DMMA_CONSUMERS) * sizeof(uint64_t);
 };
 
+// grid-wide barrier between consecutive half-steps of one persistent launch: the
+// consumers of every CTA publish "my writes of half-step h are out" on a global
+// counter; producers wait for all CTAs before they read state for half-step h+1.
+__device__ __forceinline__ void grid_arrive(unsigned long long* counter) {
+  __threadfence();
+  atomicAdd(counter, 1ull);
+}
+__device__ __forceinline__ bool grid_wait(const unsigned long long* counter, unsigned long long target, int* status) {
+  const long long t0 = clock64();
+  while (*reinterpret_cast<const volatile unsigned long long*>(counter) < target) {
+    __nanosleep(32);
+    if (clock64() - t0 > 4000000000ll) {  // ~2 s: never hang the GPU on a lost CTA
+      atomicOr(status, FLAG_COMM_TIMEOUT);
+      return false;
+    }
+  }
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other SMs -> our TMA reads
+  return true;
+}
+
 template <int KB, bool HAS_MEAN>
-__global__ void __launch_bounds__(DMMA_THREADS, 1) half_step_dense_dmma_kernel(const HalfStepArgs a) {
+__global__ void __launch_bounds__(DMMA_THREADS, 1)
+    half_step_dense_dmma_kernel(const HalfStepArgs a, const HalfDesc* __restrict__ descs, const int nhalf,
+                                unsigned long long* gbar, const unsigned long long gbar_base) {
   constexpr int D = 8 * KB;
   constexpr int RS = row_stride(KB);
   using SL = SmemLayout<KB>;
@@ -134,78 +169,93 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1) half_step_dense_dmma_kernel(c
   if (HAS_MEAN)
     for (int k = tid; k < D; k += DMMA_THREADS) sMu[k] = a.model.params[k];
   __syncthreads();
-  if (tid == 0) {  // one bulk copy brings the whole packed factor
+  if (tid == 0) {  // one bulk copy brings the whole packed factor, once per launch
     constexpr unsigned bytes = (unsigned)(SL::L_doubles * sizeof(double));
     mbar_arrive_expect_tx(barL, bytes);
     bulk_g2s(sL, a.model.chol, bytes, barL);
   }
 
-  const int i_lo = a.range ? a.range->x : a.i_lo;
-  const int i_hi = a.range ? a.range->y : a.i_hi;
-  const int64_t count = (int64_t)i_hi - i_lo;
-  const int64_t ntiles = (count + 7) >> 3;
   const int64_t tstride = (int64_t)gridDim.x * DMMA_CONSUMERS;
   const int64_t tile0 = (int64_t)blockIdx.x + (int64_t)gridDim.x * pair;  // SM-major deal
   double* slot = sSlots + (size_t)pair * SL::slot_doubles;
   double* myS = slot + (size_t)g * RS + 2 * t;  // this lane's 16-byte chunks of row g
   double* myC = myS + 8 * RS;                   // partner row, later the proposal
   TileMeta* meta = sMeta + 2 * pair;
+  unsigned k = 0;  // tiles this pair has handled so far in the launch (mbarrier phase counter)
 
   if (is_producer) {
     // ================= producer: draws, lookups, TMA row gather, proposal =================
-    const int64_t Nc = a.N - a.a_count;
     const double dm1 = (double)a.D - 1.0;
     const int row = lane & 7;
-    // per-row quantities of one tile (lanes 0..7 own rows 0..7; the other lanes mirror them)
+    // per-row quantities of one tile (every lane mirrors row lane & 7)
     struct Prep {
       int32_t w, wp;
       double zz, factor, log_u, lp_old;
       bool valid;
     };
-    auto prep = [&](int64_t tile) -> Prep {
-      Prep p;
-      int64_t i = (int64_t)i_lo + tile * 8 + row;
-      p.valid = i < i_hi;
-      if (!p.valid) i = (int64_t)i_hi - 1;
-      const u32x4 A = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_PROP_A, (uint32_t)i);
-      const double tt = __dadd_rn(__dmul_rn(__dsub_rn(a.p0, 1.0), u53(A.x, A.y)), 1.0);  // stretch.py:30
-      p.zz = __ddiv_rn(__dmul_rn(tt, tt), a.p0);
-      const int64_t r = (int64_t)bounded64(A.z, A.w, (uint64_t)Nc);  // stretch.py:32
-      p.w = __ldg(a.order + a.a_start + i);
-      p.wp = __ldg(a.order + (r < a.a_start ? r : r + a.a_count));
-      const u32x4 U = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_ACCEPT, (uint32_t)i);
-      p.log_u = log(u53(U.x, U.y));
-      p.factor = __dmul_rn(dm1, log(p.zz));  // stretch.py:31
-      p.lp_old = a.logp[p.w];                // looked up a whole tile ahead of its use
-      return p;
-    };
-    // publish the meta record and launch the 16 row copies of one tile into the landing slot
-    auto issue = [&](const Prep& p, int par) {
-      TileMeta* m = meta + par;
-      if (lane < 8) {
-        m->factor[row] = p.factor;
-        m->log_u[row] = p.log_u;
-        m->lp_old[row] = p.lp_old;
-        m->w[row] = p.valid ? p.w : -1;
+    for (int h = 0; h < nhalf; ++h) {
+      const HalfDesc d = descs[h];
+      const int32_t* order = a.order + (size_t)d.order_step * a.N;
+      const int2 rg = a.range ? a.range[(size_t)d.order_step * MAX_SPLITS + d.split] : make_int2(0, d.a_count);
+      const int i_lo = rg.x, i_hi = rg.y;
+      const int64_t ntiles = ((int64_t)i_hi - i_lo + 7) >> 3;
+      const int64_t Nc = a.N - d.a_count;
+      // draws + index lookups: independent of the walker state, so they run ahead of the grid barrier
+      auto prep = [&](int64_t tile, bool with_lp) -> Prep {
+        Prep p;
+        int64_t i = (int64_t)i_lo + tile * 8 + row;
+        p.valid = i < i_hi;
+        if (!p.valid) i = (int64_t)i_hi - 1;
+        const u32x4 A = draw_words(a.seed, d.step, (uint32_t)d.split, TAG_PROP_A, (uint32_t)i);
+        const double tt = __dadd_rn(__dmul_rn(__dsub_rn(a.p0, 1.0), u53(A.x, A.y)), 1.0);  // stretch.py:30
+        p.zz = __ddiv_rn(__dmul_rn(tt, tt), a.p0);
+        const int64_t r = (int64_t)bounded64(A.z, A.w, (uint64_t)Nc);  // stretch.py:32
+        p.w = __ldg(order + d.a_start + i);
+        p.wp = __ldg(order + (r < d.a_start ? r : r + d.a_count));
+        const u32x4 U = draw_words(a.seed, d.step, (uint32_t)d.split, TAG_ACCEPT, (uint32_t)i);
+        p.log_u = log(u53(U.x, U.y));
+        p.factor = __dmul_rn(dm1, log(p.zz));  // stretch.py:31
+        p.lp_old = with_lp ? a.logp[p.w] : 0.0;
+        return p;
+      };
+      // publish the meta record and launch the 16 row copies of one tile into the landing slot
+      auto issue = [&](Prep& p, int par, bool load_lp) {
+        if (lane == 0) mbar_arrive_expect_tx(barFull + pair, 16u * D * (unsigned)sizeof(double));
+        __syncwarp();
+        if (lane < 16) {
+          const bool partner = lane >= 8;
+          const int64_t wr = partner ? (int64_t)p.wp : (int64_t)p.w;
+          const double* base =
+              (partner && a.peer_coords != nullptr) ? a.peer_coords[wr / a.rows_per_rank] : a.coords;
+          bulk_g2s(slot + (size_t)(partner ? 8 : 0) * RS + (size_t)row * RS, base + (size_t)wr * D,
+                   (unsigned)(D * sizeof(double)), barFull + pair);
+        }
+        if (load_lp) p.lp_old = a.logp[p.w];  // behind the row copies: off the post-barrier critical path
+        TileMeta* m = meta + par;
+        if (lane < 8) {
+          m->factor[row] = p.factor;
+          m->log_u[row] = p.log_u;
+          m->lp_old[row] = p.lp_old;
+          m->w[row] = p.valid ? p.w : -1;
+        }
+      };
+      Prep cur{}, nxt{};
+      if (tile0 < ntiles) cur = prep(tile0, h == 0);
+      if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, h == 0);
+      if (h > 0) {
+        // every CTA has finished writing half-step h-1: the state may be read again
+        bool ok = true;
+        if (lane == 0) ok = grid_wait(gbar, gbar_base + (unsigned long long)h * gridDim.x, a.status);
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) return;
       }
-      if (lane == 0) mbar_arrive_expect_tx(barFull + pair, 16u * D * (unsigned)sizeof(double));
-      __syncwarp();
-      if (lane < 16) {
-        const bool partner = lane >= 8;
-        const int64_t wr = partner ? (int64_t)p.wp : (int64_t)p.w;
-        const double* base = (partner && a.peer_coords != nullptr) ? a.peer_coords[wr / a.rows_per_rank] : a.coords;
-        bulk_g2s(slot + (size_t)(partner ? 8 : 0) * RS + (size_t)row * RS, base + (size_t)wr * D,
-                 (unsigned)(D * sizeof(double)), barFull + pair);
+      if (tile0 < ntiles) {
+        // the slot was released by the consumer at the end of the previous half-step's last tile
+        if (k > 0) mbar_wait(barFree + pair, (k - 1) & 1u);
+        issue(cur, (int)(k & 1u), h > 0);
       }
-    };
-    if (tile0 < ntiles) {
-      Prep cur = prep(tile0);
-      issue(cur, 0);
-      Prep nxt = cur;
-      if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride);
-      unsigned k = 0;
       for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++k) {
-        // ---- rows of tile k have landed: form the proposal over the partner rows
+        // ---- rows of this tile have landed: form the proposal over the partner rows
         const double zz = __shfl_sync(0xffffffffu, cur.zz, g);
         mbar_wait(barFull + pair, k & 1u);
 #pragma unroll
@@ -224,8 +274,8 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1) half_step_dense_dmma_kernel(c
         if (tile + tstride < ntiles) {
           cur = nxt;
           mbar_wait(barFree + pair, k & 1u);
-          issue(cur, (int)((k + 1) & 1u));
-          if (tile + 2 * tstride < ntiles) nxt = prep(tile + 2 * tstride);
+          issue(cur, (int)((k + 1) & 1u), h > 0 && tile == tile0);
+          if (tile + 2 * tstride < ntiles) nxt = prep(tile + 2 * tstride, true);
         }
       }
     }
@@ -233,106 +283,142 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1) half_step_dense_dmma_kernel(c
   }
 
   // ================================ consumer: DMMA, accept, update ================================
+  // optional per-tile timestamps of the LAST half-step (cycles since this warp entered the kernel):
+  // 1 wait start, 2 proposal ready, 3 proposal in registers, 4 DMMA block done, 5 tile done
+  const long long t_entry = clock64();
+  long long* tl = a.timeline ? a.timeline + ((size_t)blockIdx.x * DMMA_CONSUMERS + pair) * TL_TILES * TL_EVENTS : nullptr;
   mbar_wait(barL, 0);
-  unsigned k = 0;
-  for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++k) {
-    const TileMeta* m = meta + (k & 1u);
-    mbar_wait(barReady + pair, k & 1u);
-    double q[2 * KB];
+  for (int h = 0; h < nhalf; ++h) {
+    const HalfDesc d = descs[h];
+    const int2 rg = a.range ? a.range[(size_t)d.order_step * MAX_SPLITS + d.split] : make_int2(0, d.a_count);
+    const int64_t ntiles = ((int64_t)rg.y - rg.x + 7) >> 3;
+    unsigned kk = 0;
+    for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++k, ++kk) {
+      const TileMeta* m = meta + (k & 1u);
+      long long* tlk = (tl && h == nhalf - 1 && kk < TL_TILES && lane == 0) ? tl + kk * TL_EVENTS : nullptr;
+      if (tlk) {
+        tlk[0] = (long long)tile;
+        tlk[1] = clock64() - t_entry;
+      }
+      mbar_wait(barReady + pair, k & 1u);
+      if (tlk) tlk[2] = clock64() - t_entry;
+      double q[2 * KB];
 #pragma unroll
-    for (int j = 0; j < KB; ++j) {
-      const double2 q2 = *reinterpret_cast<const double2*>(myC + 8 * j);
-      q[2 * j + 0] = q2.x;
-      q[2 * j + 1] = q2.y;
-    }
-    const int32_t w = m->w[g];
-    const double factor = m->factor[g], log_u = m->log_u[g], lp_old = m->lp_old[g];
-    __syncwarp();
-    if (lane == 0) mbar_arrive(barFree + pair);  // slot and meta may be refilled while this tile computes
+      for (int j = 0; j < KB; ++j) {
+        const double2 q2 = *reinterpret_cast<const double2*>(myC + 8 * j);
+        q[2 * j + 0] = q2.x;
+        q[2 * j + 1] = q2.y;
+      }
+      const int32_t w = m->w[g];
+      const double factor = m->factor[g], log_u = m->log_u[g], lp_old = m->lp_old[g];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(barFree + pair);  // slot and meta may be refilled while this tile computes
+      if (tlk) tlk[3] = clock64() - t_entry;
 
-    // ---- y = L^T (q - mu) block by block on the tensor pipe; rs = sum_n y_n^2
-    double rs = 0.0;
-    const double* bptr = sL + lane;
+      // ---- y = L^T (q - mu) block by block on the tensor pipe; rs = sum_n y_n^2
+      double rs = 0.0;
+      const double* bptr = sL + 2 * lane;  // one 16-byte load feeds the two k-halves of a block pair
 #pragma unroll
-    for (int nb0 = 0; nb0 < KB; nb0 += NI) {
-      double c[NI][2][2];
+      for (int nb0 = 0; nb0 < KB; nb0 += NI) {
+        double c[NI][2][2];
 #pragma unroll
-      for (int n = 0; n < NI; ++n) c[n][0][0] = c[n][0][1] = c[n][1][0] = c[n][1][1] = 0.0;
+        for (int n = 0; n < NI; ++n) c[n][0][0] = c[n][0][1] = c[n][1][0] = c[n][1][1] = 0.0;
 #pragma unroll
-      for (int j = nb0; j < KB; ++j) {
-        double x0 = q[2 * j + 0], x1 = q[2 * j + 1];
-        if (HAS_MEAN) {
-          const double2 m2 = *reinterpret_cast<const double2*>(sMu + 8 * j + 2 * t);
-          x0 -= m2.x;
-          x1 -= m2.y;
+        for (int j = nb0; j < KB; ++j) {
+          double x0 = q[2 * j + 0], x1 = q[2 * j + 1];
+          if (HAS_MEAN) {
+            const double2 m2 = *reinterpret_cast<const double2*>(sMu + 8 * j + 2 * t);
+            x0 -= m2.x;
+            x1 -= m2.y;
+          }
+#pragma unroll
+          for (int n = 0; n < NI; ++n) {
+            if (nb0 + n < KB && j >= nb0 + n) {
+              const double2 b2 = *reinterpret_cast<const double2*>(bptr);
+              dmma884(c[n][0][0], c[n][0][1], x0, b2.x);
+              dmma884(c[n][1][0], c[n][1][1], x1, b2.y);
+              bptr += 64;
+            }
+          }
         }
 #pragma unroll
         for (int n = 0; n < NI; ++n) {
-          if (nb0 + n < KB && j >= nb0 + n) {
-            dmma884(c[n][0][0], c[n][0][1], x0, bptr[0]);
-            dmma884(c[n][1][0], c[n][1][1], x1, bptr[32]);
-            bptr += 64;
-          }
+          const double y0 = c[n][0][0] + c[n][1][0], y1 = c[n][0][1] + c[n][1][1];
+          rs = fma(y0, y0, rs);
+          rs = fma(y1, y1, rs);
         }
       }
-#pragma unroll
-      for (int n = 0; n < NI; ++n) {
-        const double y0 = c[n][0][0] + c[n][1][0], y1 = c[n][0][1] + c[n][1][1];
-        rs = fma(y0, y0, rs);
-        rs = fma(y1, y1, rs);
-      }
-    }
-    rs += __shfl_xor_sync(0xffffffffu, rs, 1);
-    rs += __shfl_xor_sync(0xffffffffu, rs, 2);
-    const double lp_new = -0.5 * rs;
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+      const double lp_new = -0.5 * rs;
+      if (tlk) tlk[4] = clock64() - t_entry;
 
-    // ---- guards (ensemble.py:476-479, 550-551): a non-finite lp is the only way
-    // a non-finite coordinate can show, so the element scan is off the fast path
-    if (!isfinite(lp_new)) {
-      bool any_inf = false, any_nan = false;
+      // ---- guards (ensemble.py:476-479, 550-551): a non-finite lp is the only way
+      // a non-finite coordinate can show, so the element scan is off the fast path
+      if (!isfinite(lp_new)) {
+        bool any_inf = false, any_nan = false;
 #pragma unroll
-      for (int kk = 0; kk < 2 * KB; ++kk) {
-        any_inf |= isinf(q[kk]);
-        any_nan |= isnan(q[kk]);
+        for (int e = 0; e < 2 * KB; ++e) {
+          any_inf |= isinf(q[e]);
+          any_nan |= isnan(q[e]);
+        }
+        if (any_inf) atomicOr(a.status, FLAG_INF_PARAM);
+        if (any_nan) atomicOr(a.status, FLAG_NAN_PARAM);
+        if (isnan(lp_new)) atomicOr(a.status, FLAG_NAN_LOGPROB);
       }
-      if (any_inf) atomicOr(a.status, FLAG_INF_PARAM);
-      if (any_nan) atomicOr(a.status, FLAG_NAN_PARAM);
-      if (isnan(lp_new)) atomicOr(a.status, FLAG_NAN_LOGPROB);
-    }
 
-    // ---- Metropolis accept + in-place update (red_blue.py:96-104, move.py:29-34)
-    const double lnpdiff = __dsub_rn(__dadd_rn(factor, lp_new), lp_old);
-    const bool acc = (w >= 0) && (lnpdiff > log_u);
-    if (acc) {
-      double* dst = a.coords + (size_t)w * D + 2 * t;
-#pragma unroll
-      for (int j = 0; j < KB; ++j) *reinterpret_cast<double2*>(dst + 8 * j) = make_double2(q[2 * j], q[2 * j + 1]);
-    }
-    if (w >= 0 && t == 0) {
+      // ---- Metropolis accept + in-place update (red_blue.py:96-104, move.py:29-34)
+      const double lnpdiff = __dsub_rn(__dadd_rn(factor, lp_new), lp_old);
+      const bool acc = (w >= 0) && (lnpdiff > log_u);
       if (acc) {
-        a.logp[w] = lp_new;
-        atomicAdd(a.nacc + w, 1ull);  // RED: fire and forget
+        double* dst = a.coords + (size_t)w * D + 2 * t;
+#pragma unroll
+        for (int j = 0; j < KB; ++j) *reinterpret_cast<double2*>(dst + 8 * j) = make_double2(q[2 * j], q[2 * j + 1]);
       }
-      a.accepted[w] = acc ? 1 : 0;
+      if (w >= 0 && t == 0) {
+        if (acc) {
+          a.logp[w] = lp_new;
+          atomicAdd(a.nacc + w, 1ull);  // RED: fire and forget
+        }
+        a.accepted[w] = acc ? 1 : 0;
+      }
+      if (tlk) tlk[5] = clock64() - t_entry;
+    }
+    if (h + 1 < nhalf) {
+      // this CTA's updates of half-step h are out: tell the grid (consumer warps only, named barrier 1)
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * DMMA_CONSUMERS) : "memory");
+      if (tid == 0) grid_arrive(gbar);
     }
   }
 }
 
 template <int KB>
-cudaError_t launch_t(const HalfStepArgs& a, int sm_count, cudaStream_t st) {
+cudaError_t launch_t(const HalfStepArgs& a, const HalfDesc* descs_dev, int nhalf, int max_count,
+                     unsigned long long* gbar, unsigned long long gbar_base, int sm_count, int* grid_out,
+                     cudaStream_t st) {
   const size_t smem = SmemLayout<KB>::total_bytes;
   const bool has_mean = a.model.s0 != 0.0;  // set by eb_model_set when mu != 0
   auto kern = has_mean ? half_step_dense_dmma_kernel<KB, true> : half_step_dense_dmma_kernel<KB, false>;
-  if (smem > 48 * 1024) {
+  static bool configured[2] = {false, false};
+  if (!configured[has_mean]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    configured[has_mean] = true;
   }
-  const int64_t count = (int64_t)a.i_hi - a.i_lo;
-  if (count <= 0) return cudaSuccess;
-  const int64_t ntiles = (count + 7) / 8;
+  *grid_out = 0;
+  if (max_count <= 0 || nhalf <= 0) return cudaSuccess;
+  const int64_t ntiles = ((int64_t)max_count + 7) / 8;
   const int grid = (int)(ntiles < sm_count ? ntiles : sm_count);
-  kern<<<grid, DMMA_THREADS, smem, st>>>(a);
-  return cudaGetLastError();
+  *grid_out = grid;
+  HalfStepArgs args = a;
+  void* params[] = {(void*)&args, (void*)&descs_dev, (void*)&nhalf, (void*)&gbar, (void*)&gbar_base};
+  if (nhalf == 1) {  // no grid barrier inside: a plain launch (cooperative launches cost ~2 us more each)
+    kern<<<grid, DMMA_THREADS, smem, st>>>(args, descs_dev, nhalf, gbar, gbar_base);
+    return cudaGetLastError();
+  }
+  // cooperative launch: the grid barrier between half-steps needs every CTA resident
+  return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(DMMA_THREADS), params, smem, st);
 }
 
 }  // namespace
@@ -364,28 +450,30 @@ void dense_dmma_pack_factor(const double* L, int D, double* packed) {
       for (int n = 0; n < NI; ++n) {
         const int nb = nb0 + n;
         if (nb >= KB || j < nb) continue;
-        for (int half = 0; half < 2; ++half)
-          for (int lane = 0; lane < 32; ++lane) {
+        for (int lane = 0; lane < 32; ++lane)
+          for (int half = 0; half < 2; ++half) {  // the two k-halves of a lane sit side by side (one LDS.128)
             const int g = lane >> 2, t = lane & 3;
             packed[idx++] = L[(size_t)(8 * j + 2 * t + half) * D + (8 * nb + g)];
           }
       }
 }
 
-cudaError_t launch_half_step_dense_dmma(const HalfStepArgs& a, int sm_count, cudaStream_t st) {
+cudaError_t launch_dense_dmma(const HalfStepArgs& a, const HalfDesc* descs_dev, int nhalf, int max_count,
+                              unsigned long long* gbar, unsigned long long gbar_base, int sm_count, int* grid_out,
+                              cudaStream_t st) {
   switch (a.D) {
     case 16:
-      return launch_t<2>(a, sm_count, st);
+      return launch_t<2>(a, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
     case 32:
-      return launch_t<4>(a, sm_count, st);
+      return launch_t<4>(a, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
     case 48:
-      return launch_t<6>(a, sm_count, st);
+      return launch_t<6>(a, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
     case 64:
-      return launch_t<8>(a, sm_count, st);
+      return launch_t<8>(a, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
     case 96:
-      return launch_t<12>(a, sm_count, st);
+      return launch_t<12>(a, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
     case 128:
-      return launch_t<16>(a, sm_count, st);
+      return launch_t<16>(a, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
   }
   return cudaErrorNotSupported;
 }

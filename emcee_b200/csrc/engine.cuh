@@ -13,6 +13,7 @@ namespace eb {
 
 constexpr int MAX_SPLITS = 32;      // split_table_kernel uses one warp per set
 constexpr int TABLE_THREADS = 1024;
+constexpr int TL_TILES = 8, TL_EVENTS = 6;  // dense_dmma timeline buffer shape
 
 // device status flags (OR-ed by kernels, read back after every call)
 enum : int {
@@ -60,6 +61,7 @@ struct HalfStepArgs {
   double* tap_scalar;     // [N]
   double* tap_u;          // [N]
   int64_t* tap_active;    // [N]
+  long long* timeline;    // dense_dmma instrumentation: [SM][consumer][tile<=TL_TILES][TL_EVENTS] cycles, or null
 };
 
 struct Engine;  // defined in capi.cu
@@ -77,7 +79,19 @@ cudaError_t launch_logprob_generic(const ModelDev& m, const double* x, int64_t r
 bool dense_dmma_supported(int D);
 size_t dense_dmma_factor_doubles(int D);
 void dense_dmma_pack_factor(const double* L, int D, double* packed);  // host
-cudaError_t launch_half_step_dense_dmma(const HalfStepArgs& a, int sm_count, cudaStream_t st);
+// one half-step of a persistent dense_dmma launch
+struct HalfDesc {
+  uint64_t step;       // sampler step index (Philox counter)
+  int32_t order_step;  // which split table of the chunk (also indexes `range`)
+  int32_t split;
+  int32_t a_start, a_count;
+};
+// runs `nhalf` consecutive half-steps in ONE cooperative launch (grid barrier between them);
+// a.order / a.range point at the chunk's table bases.  max_count bounds the active ranks per
+// half-step (grid sizing).  gbar is a monotonic global counter, gbar_base its value at launch.
+cudaError_t launch_dense_dmma(const HalfStepArgs& a, const HalfDesc* descs_dev, int nhalf, int max_count,
+                              unsigned long long* gbar, unsigned long long gbar_base, int sm_count, int* grid_out,
+                              cudaStream_t st);
 
 inline int lanes_per_walker(int D) {
   int g = 4;

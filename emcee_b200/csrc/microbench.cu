@@ -124,6 +124,48 @@ __global__ void dmma884_smem_kernel(double* out, int iters, double x) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// same consumer loop with the B fragments double-buffered in registers: the G 16-byte
+// loads of group i+1 are issued before the 2G DMMAs of group i
+template <int G>
+__global__ void dmma884_smem_pf_kernel(double* out, int iters, double x) {
+  extern __shared__ double sb[];
+  for (int k = threadIdx.x; k < 8704; k += blockDim.x) sb[k] = 1e-9 * k;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  double a[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) a[k] = x + 1e-9 * (k + lane);
+  double c0[4], c1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c0[k] = c1[k] = 0.0;
+  constexpr int NG = 128 / G;  // groups per pass (128 LDS.128 = 256 DMMAs per pass)
+  for (int it = 0; it < iters; ++it) {
+    const double2* bp = reinterpret_cast<const double2*>(sb) + lane;
+    double2 cur[G], nxt[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) cur[k] = bp[32 * k];
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+      if (gi + 1 < NG) {
+#pragma unroll
+        for (int k = 0; k < G; ++k) nxt[k] = bp[32 * ((gi + 1) * G + k)];
+      }
+#pragma unroll
+      for (int k = 0; k < G; ++k) {
+        const int j = gi * G + k;
+        dmma884(c0[(2 * j) % 4], c1[(2 * j) % 4], a[(2 * j) % 32], cur[k].x);
+        dmma884(c0[(2 * j + 1) % 4], c1[(2 * j + 1) % 4], a[(2 * j + 1) % 32], cur[k].y);
+      }
+#pragma unroll
+      for (int k = 0; k < G; ++k) cur[k] = nxt[k];
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s += c0[k] + c1[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <int CH>
 __global__ void dmma1688_smem_kernel(double* out, int iters, double x) {
   extern __shared__ double sb[];
@@ -233,6 +275,23 @@ extern "C" int eb_microbench(int what, int warps_per_sm, double* result) {
       else
         ms = time_ms([&] { dmma1688_smem_kernel<2><<<blocks, threads, smem>>>(out, it2, 1.0000001); }, 5);
       flops = nwarps * it2 * (what <= 6 ? 256 * 512.0 : 128 * 2048.0);
+      break;
+    }
+    case 9:     // DMMA m8n8k4, B from smem, double-buffered 4 x LDS.128 ahead
+    case 10:    // ... 8 ahead
+    case 11: {  // ... 16 ahead
+      const int it2 = 64;
+      const size_t smem = 8704 * sizeof(double);
+      cudaFuncSetAttribute(dmma884_smem_pf_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(dmma884_smem_pf_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(dmma884_smem_pf_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (what == 9)
+        ms = time_ms([&] { dmma884_smem_pf_kernel<4><<<blocks, threads, smem>>>(out, it2, 1.0000001); }, 5);
+      else if (what == 10)
+        ms = time_ms([&] { dmma884_smem_pf_kernel<8><<<blocks, threads, smem>>>(out, it2, 1.0000001); }, 5);
+      else
+        ms = time_ms([&] { dmma884_smem_pf_kernel<16><<<blocks, threads, smem>>>(out, it2, 1.0000001); }, 5);
+      flops = nwarps * it2 * 256 * 512.0;
       break;
     }
     case 4: {  // HBM copy, 1 GiB read + 1 GiB write

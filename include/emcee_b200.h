@@ -147,9 +147,15 @@ int eb_last_step_timing(const eb_ctx* ctx, double* ms, uint64_t* launches);
  * (x3 for partners); *nactive returns the count. */
 int eb_debug_taps(eb_ctx* ctx, int64_t* partners, double* scalar, double* u_accept,
                   int64_t* active, int64_t* nactive);
+/* per-tile cycle stamps of the dense_dmma consumers during the LAST half-step
+ * launched (option "dmma_timeline"): [SM][8 consumers][8 tiles][6 events]. */
+int eb_debug_timeline(eb_ctx* ctx, int64_t* out, size_t capacity, size_t* written);
 /* engine options: "debug_taps" (0/1: record the draws of each half-step for
  * eb_debug_taps; forces the generic kernel), "dense_dmma" (0/1: allow the
- * FP64 tensor-core kernel for stretch + gauss_dense; default 1), "l2_flush"
+ * FP64 tensor-core kernel for stretch + gauss_dense; default 1), "dmma_group" (n >= 1: half-steps
+ * fused into one persistent cooperative launch of that kernel, separated by an
+ * in-kernel grid barrier; default 1), "dmma_timeline" (0/1: record consumer cycle stamps
+ * for eb_debug_timeline), "l2_flush"
  * (0/1: benchmark hygiene -- write a 256 MiB buffer before every step and time
  * each step with its own CUDA-event pair, so eb_last_step_timing excludes the
  * flush). */
