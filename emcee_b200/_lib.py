@@ -14,7 +14,8 @@ import numpy as np
 __all__ = ["lib", "Engine", "EngineError", "device_count", "LIB_PATH", "EbMove"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libemcee_b200.so")
+# EMCEE_B200_LIB: developer override (A/B of two builds); the product always loads the in-tree library
+LIB_PATH = os.environ.get("EMCEE_B200_LIB") or os.path.join(HERE, "libemcee_b200.so")
 
 EB_OK = 0
 EB_ERR_INVALID = -1
@@ -106,6 +107,8 @@ def lib():
             )
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
+            if os.environ.get("EMCEE_B200_LIB") and not hasattr(handle, name):
+                continue  # A/B against an older build
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args

@@ -550,7 +550,7 @@ int flush_dmma(eb_ctx* c, const eb_move& mv, DmmaGroup& grp, uint64_t& launches)
   int bound = grp.max_count;
   if (c->comm.nranks > 1 && c->comm.rows_per_rank < bound) bound = (int)c->comm.rows_per_rank;
   int grid = 0;
-  CK(c, launch_dense_dmma(a, c->descs_dev + grp.first, grp.nhalf, bound, c->gbar, c->gbar_count, c->sm_count, &grid,
+  CK(c, launch_dense_dmma(a, c->descs_host[grp.first], c->descs_dev + grp.first, grp.nhalf, bound, c->gbar, c->gbar_count, c->sm_count, &grid,
                           c->st));
   c->gbar_count += (unsigned long long)(grp.nhalf - 1) * (unsigned long long)grid;
   c->last_kernel = "dense_dmma";

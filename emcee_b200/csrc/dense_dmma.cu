@@ -136,8 +136,8 @@ __device__ __forceinline__ bool grid_wait(const unsigned long long* counter, uns
 
 template <int KB, bool HAS_MEAN>
 __global__ void __launch_bounds__(DMMA_THREADS, 1)
-    half_step_dense_dmma_kernel(const HalfStepArgs a, const HalfDesc* __restrict__ descs, const int nhalf,
-                                unsigned long long* gbar, const unsigned long long gbar_base) {
+    half_step_dense_dmma_kernel(const HalfStepArgs a, const HalfDesc d0, const HalfDesc* __restrict__ descs,
+                                const int nhalf, unsigned long long* gbar, const unsigned long long gbar_base) {
   constexpr int D = 8 * KB;
   constexpr int RS = row_stride(KB);
   using SL = SmemLayout<KB>;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
       bool valid;
     };
     for (int h = 0; h < nhalf; ++h) {
-      const HalfDesc d = descs[h];
+      const HalfDesc d = (h == 0) ? d0 : descs[h];  // the first one travels in the launch parameters
       const int32_t* order = a.order + (size_t)d.order_step * a.N;
       const int2 rg = a.range ? a.range[(size_t)d.order_step * MAX_SPLITS + d.split] : make_int2(0, d.a_count);
       const int i_lo = rg.x, i_hi = rg.y;
@@ -241,18 +241,22 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
       };
       Prep cur{}, nxt{};
       if (tile0 < ntiles) cur = prep(tile0, h == 0);
-      if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, h == 0);
-      if (h > 0) {
+      if (h == 0) {
+        // launch start: get the first rows moving before anything else
+        if (tile0 < ntiles) issue(cur, (int)(k & 1u), false);
+        if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, true);
+      } else {
+        if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, false);
         // every CTA has finished writing half-step h-1: the state may be read again
         bool ok = true;
         if (lane == 0) ok = grid_wait(gbar, gbar_base + (unsigned long long)h * gridDim.x, a.status);
         ok = __shfl_sync(0xffffffffu, ok, 0);
         if (!ok) return;
-      }
-      if (tile0 < ntiles) {
-        // the slot was released by the consumer at the end of the previous half-step's last tile
-        if (k > 0) mbar_wait(barFree + pair, (k - 1) & 1u);
-        issue(cur, (int)(k & 1u), h > 0);
+        if (tile0 < ntiles) {
+          // the slot was released by the consumer at the end of the previous half-step's last tile
+          if (k > 0) mbar_wait(barFree + pair, (k - 1) & 1u);
+          issue(cur, (int)(k & 1u), true);
+        }
       }
       for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++k) {
         // ---- rows of this tile have landed: form the proposal over the partner rows
@@ -289,7 +293,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   long long* tl = a.timeline ? a.timeline + ((size_t)blockIdx.x * DMMA_CONSUMERS + pair) * TL_TILES * TL_EVENTS : nullptr;
   mbar_wait(barL, 0);
   for (int h = 0; h < nhalf; ++h) {
-    const HalfDesc d = descs[h];
+    const HalfDesc d = (h == 0) ? d0 : descs[h];
     const int2 rg = a.range ? a.range[(size_t)d.order_step * MAX_SPLITS + d.split] : make_int2(0, d.a_count);
     const int64_t ntiles = ((int64_t)rg.y - rg.x + 7) >> 3;
     unsigned kk = 0;
@@ -394,7 +398,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
 }
 
 template <int KB>
-cudaError_t launch_t(const HalfStepArgs& a, const HalfDesc* descs_dev, int nhalf, int max_count,
+cudaError_t launch_t(const HalfStepArgs& a, const HalfDesc& d0, const HalfDesc* descs_dev, int nhalf, int max_count,
                      unsigned long long* gbar, unsigned long long gbar_base, int sm_count, int* grid_out,
                      cudaStream_t st) {
   const size_t smem = SmemLayout<KB>::total_bytes;
@@ -412,9 +416,10 @@ cudaError_t launch_t(const HalfStepArgs& a, const HalfDesc* descs_dev, int nhalf
   const int grid = (int)(ntiles < sm_count ? ntiles : sm_count);
   *grid_out = grid;
   HalfStepArgs args = a;
-  void* params[] = {(void*)&args, (void*)&descs_dev, (void*)&nhalf, (void*)&gbar, (void*)&gbar_base};
+  HalfDesc first = d0;
+  void* params[] = {(void*)&args, (void*)&first, (void*)&descs_dev, (void*)&nhalf, (void*)&gbar, (void*)&gbar_base};
   if (nhalf == 1) {  // no grid barrier inside: a plain launch (cooperative launches cost ~2 us more each)
-    kern<<<grid, DMMA_THREADS, smem, st>>>(args, descs_dev, nhalf, gbar, gbar_base);
+    kern<<<grid, DMMA_THREADS, smem, st>>>(args, first, descs_dev, nhalf, gbar, gbar_base);
     return cudaGetLastError();
   }
   // cooperative launch: the grid barrier between half-steps needs every CTA resident
@@ -440,8 +445,8 @@ size_t dense_dmma_factor_doubles(int D) { return (size_t)packed_blocks(D / 8) * 
 
 // L: row-major lower-triangular factor (A = L L^T).  Packed in the order the
 // kernel consumes it: for each group of NI 8-column tiles, for each 8-row group
-// j, for each tile nb of the group with j >= nb, two 4x8 fragments (half = 0, 1)
-// whose lane (g, t) element is L[8j + 2t + half][8nb + g].
+// j, for each tile nb of the group with j >= nb, the two 4x8 fragments (half = 0, 1)
+// interleaved per lane: lane (g, t) holds L[8j + 2t + half][8nb + g], half = 0, 1 side by side.
 void dense_dmma_pack_factor(const double* L, int D, double* packed) {
   const int KB = D / 8;
   size_t idx = 0;
@@ -458,22 +463,23 @@ void dense_dmma_pack_factor(const double* L, int D, double* packed) {
       }
 }
 
-cudaError_t launch_dense_dmma(const HalfStepArgs& a, const HalfDesc* descs_dev, int nhalf, int max_count,
+cudaError_t launch_dense_dmma(const HalfStepArgs& a, const HalfDesc& d0, const HalfDesc* descs_dev, int nhalf,
+                              int max_count,
                               unsigned long long* gbar, unsigned long long gbar_base, int sm_count, int* grid_out,
                               cudaStream_t st) {
   switch (a.D) {
     case 16:
-      return launch_t<2>(a, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
+      return launch_t<2>(a, d0, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
     case 32:
-      return launch_t<4>(a, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
+      return launch_t<4>(a, d0, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
     case 48:
-      return launch_t<6>(a, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
+      return launch_t<6>(a, d0, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
     case 64:
-      return launch_t<8>(a, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
+      return launch_t<8>(a, d0, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
     case 96:
-      return launch_t<12>(a, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
+      return launch_t<12>(a, d0, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
     case 128:
-      return launch_t<16>(a, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
+      return launch_t<16>(a, d0, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
   }
   return cudaErrorNotSupported;
 }

@@ -87,9 +87,10 @@ struct HalfDesc {
   int32_t a_start, a_count;
 };
 // runs `nhalf` consecutive half-steps in ONE cooperative launch (grid barrier between them);
-// a.order / a.range point at the chunk's table bases.  max_count bounds the active ranks per
+// a.order / a.range point at the chunk's table bases; d0 == descs[0] travels by value.  max_count bounds the active ranks per
 // half-step (grid sizing).  gbar is a monotonic global counter, gbar_base its value at launch.
-cudaError_t launch_dense_dmma(const HalfStepArgs& a, const HalfDesc* descs_dev, int nhalf, int max_count,
+cudaError_t launch_dense_dmma(const HalfStepArgs& a, const HalfDesc& d0, const HalfDesc* descs_dev, int nhalf,
+                              int max_count,
                               unsigned long long* gbar, unsigned long long gbar_base, int sm_count, int* grid_out,
                               cudaStream_t st);
 
