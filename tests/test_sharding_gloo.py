@@ -29,7 +29,7 @@ def _moves(rb, spec):
     }[spec]()
 
 
-def _worker(rank, world, port, case, out):
+def _worker(rank, world, port, cases, out):
     sys.path.insert(0, ROOT)
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch
@@ -40,26 +40,26 @@ def _worker(rank, world, port, case, out):
     from oracle import targets as T
 
     rdv = dist.Rendezvous("gloo")
-    name, N, D, moves, steps = case
-    target, p0 = T.make_config(name, N, D)
-    o = rb.OracleSampler(N, D, target, _moves(rb, moves), seed=77)
-    o.set_state(p0)
-    w_lo, w_hi = dist.row_block(N, rank, world)
-    o.owner_range = (w_lo, w_hi)
+    for ci, (name, N, D, moves, steps) in enumerate(cases):
+        target, p0 = T.make_config(name, N, D)
+        o = rb.OracleSampler(N, D, target, _moves(rb, moves), seed=77)
+        o.set_state(p0)
+        w_lo, w_hi = dist.row_block(N, rank, world)
+        o.owner_range = (w_lo, w_hi)
 
-    def exchange(coords, log_prob, accepted):
-        # what ncclAllGather does in place on the device: every rank contributes its row block
-        for arr in (coords, log_prob, accepted):
-            t = torch.from_numpy(np.ascontiguousarray(arr[w_lo:w_hi]))
-            parts = [torch.empty_like(t) for _ in range(world)]
-            td.all_gather(parts, t)
-            for r, p in enumerate(parts):
-                lo, hi = dist.row_block(N, r, world)
-                arr[lo:hi] = p.numpy()
+        def exchange(coords, log_prob, accepted, N=N, w_lo=w_lo, w_hi=w_hi):
+            # what ncclAllGather does in place on the device: every rank contributes its row block
+            for arr in (coords, log_prob, accepted):
+                t = torch.from_numpy(np.ascontiguousarray(arr[w_lo:w_hi]))
+                parts = [torch.empty_like(t) for _ in range(world)]
+                td.all_gather(parts, t)
+                for r, p in enumerate(parts):
+                    lo, hi = dist.row_block(N, r, world)
+                    arr[lo:hi] = p.numpy()
 
-    o.exchange = exchange
-    o.run(steps)
-    np.savez(out % rank, coords=o.coords, log_prob=o.log_prob)
+        o.exchange = exchange
+        o.run(steps)
+        np.savez(out % (ci, rank), coords=o.coords, log_prob=o.log_prob)
     rdv.close()
 
 
@@ -70,24 +70,25 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_two_ranks_reproduce_one(case, tmp_path):
+def test_two_ranks_reproduce_one(tmp_path):
+    """One pair of gloo processes runs every case (importing torch in a fresh
+    process dominates the cost)."""
     import torch.multiprocessing as mp
 
     from oracle import redblue as rb
     from oracle import targets as T
 
-    name, N, D, moves, steps = case
-    out = str(tmp_path / "rank%d.npz")
-    mp.spawn(_worker, args=(2, _free_port(), case, out), nprocs=2, join=True)
-    target, p0 = T.make_config(name, N, D)
-    ref = rb.OracleSampler(N, D, target, _moves(rb, moves), seed=77)
-    ref.set_state(p0)
-    ref.run(steps)
-    for rank in range(2):
-        got = np.load(out % rank)
-        assert np.array_equal(got["coords"], ref.coords)
-        assert np.array_equal(got["log_prob"], ref.log_prob)
+    out = str(tmp_path / "case%d_rank%d.npz")
+    mp.spawn(_worker, args=(2, _free_port(), CASES, out), nprocs=2, join=True)
+    for ci, (name, N, D, moves, steps) in enumerate(CASES):
+        target, p0 = T.make_config(name, N, D)
+        ref = rb.OracleSampler(N, D, target, _moves(rb, moves), seed=77)
+        ref.set_state(p0)
+        ref.run(steps)
+        for rank in range(2):
+            got = np.load(out % (ci, rank))
+            assert np.array_equal(got["coords"], ref.coords), (name, rank)
+            assert np.array_equal(got["log_prob"], ref.log_prob), (name, rank)
 
 
 def test_active_range_matches_definition():
