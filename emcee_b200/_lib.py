@@ -90,6 +90,7 @@ _SIGNATURES = {
     "eb_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int]),
     "eb_comm_export": (C.c_int, [C.c_void_p, C.c_char_p]),
     "eb_comm_import": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "eb_comm_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp]),
 }
 
 _lib = None
@@ -341,6 +342,11 @@ class Engine(object):
         buf = C.create_string_buffer(EB_IPC_BLOB_BYTES)
         self._check(lib().eb_comm_export(self._h, buf))
         return buf.raw
+
+    def comm_probe(self, peer, what):
+        out = C.c_double()
+        self._check(lib().eb_comm_probe(self._h, int(peer), int(what), C.byref(out)))
+        return float(out.value)
 
     def comm_import(self, blobs):
         self._check(lib().eb_comm_import(self._h, blobs))

@@ -70,6 +70,7 @@ struct eb_ctx {
   uint64_t last_launches = 0;
   const char* last_kernel = "none";
   bool allow_dmma = true;
+  bool fused_last = false;  // the last dense_dmma launch carried the P2P barrier itself
   int dmma_group = 1;  // half-steps per persistent dense_dmma launch (1: a launch per half-step)
 
   Comm comm;  // multi-GPU (comm.h)
@@ -549,6 +550,8 @@ int flush_dmma(eb_ctx* c, const eb_move& mv, DmmaGroup& grp, uint64_t& launches)
   a.range = c->comm.nranks > 1 ? c->comm.ranges : nullptr;
   int bound = grp.max_count;
   if (c->comm.nranks > 1 && c->comm.rows_per_rank < bound) bound = (int)c->comm.rows_per_rank;
+  const bool fused = grp.nhalf == 1 && comm_fuse_barrier(c->comm, a);  // P2P: barrier inside the kernel
+  c->fused_last = fused;
   int grid = 0;
   CK(c, launch_dense_dmma(a, c->descs_host[grp.first], c->descs_dev + grp.first, grp.nhalf, bound, c->gbar, c->gbar_count, c->sm_count, &grid,
                           c->st));
@@ -645,7 +648,7 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
           if (multi) {  // ranks exchange rows after every split: one half-step per launch
             rc = flush_dmma(c, mv, grp, launches);
             if (rc) return rc;
-            if (comm_after_split(c->comm, c->st, c->status_dev, launches))
+            if (!c->fused_last && comm_after_split(c->comm, c->st, c->status_dev, launches))
               FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
           }
         }
@@ -901,6 +904,13 @@ int eb_comm_export(eb_ctx* c, char blob[EB_IPC_BLOB_BYTES]) {
   if (!c) return EB_ERR_INVALID;
   CK(c, cudaSetDevice(c->device));
   if (comm_export(c->comm, blob)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+  return EB_OK;
+}
+
+int eb_comm_probe(eb_ctx* c, int peer, int what, double* gbs) {
+  if (!c || !gbs) return EB_ERR_INVALID;
+  CK(c, cudaSetDevice(c->device));
+  if (comm_probe(c->comm, peer, what, c->D, c->st, gbs)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
   return EB_OK;
 }
 

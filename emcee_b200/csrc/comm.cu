@@ -88,6 +88,66 @@ __global__ void p2p_barrier_kernel(unsigned* const* peer_flags, volatile unsigne
   }
 }
 
+// ---- peer-memory read probes (eb_comm_probe): what NVLink delivers for our access patterns ----
+__global__ void probe_stream_kernel(const double2* __restrict__ src, size_t n16, double* sink) {
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const double2 v = __ldcg(src + i);
+    acc += v.x + v.y;
+  }
+  if (acc == 123.456) *sink = acc;
+}
+// each warp reads whole rows of `row16` 16-byte chunks at pseudo-random row indices
+__global__ void probe_rows_kernel(const double2* __restrict__ src, size_t nrows, int row16, int rows_per_warp,
+                                  double* sink) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double acc = 0.0;
+  for (int k = 0; k < rows_per_warp; ++k) {
+    const size_t r = (size_t)fmix32((uint32_t)(warp * 7919u + k * 104729u + 17u)) % nrows;
+    for (int c = lane; c < row16; c += 32) {
+      const double2 v = __ldcg(src + r * row16 + c);
+      acc += v.x + v.y;
+    }
+  }
+  if (acc == 123.456) *sink = acc;
+}
+// same rows through TMA bulk copies into shared memory (what dense_dmma's producers do)
+__global__ void probe_bulk_kernel(const double* __restrict__ src, size_t nrows, int row_doubles, int rows_per_warp,
+                                  double* sink) {
+  extern __shared__ __align__(16) unsigned char psm[];
+  const int lane = threadIdx.x & 31, warp_in = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  double* buf = reinterpret_cast<double*>(psm) + (size_t)warp_in * 16 * row_doubles;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(psm + (size_t)nw * 16 * row_doubles * sizeof(double)) + warp_in;
+  const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bar);
+  if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const size_t warp = (size_t)blockIdx.x * nw + warp_in;
+  const unsigned bytes = (unsigned)(row_doubles * sizeof(double));
+  for (int k = 0; k < rows_per_warp / 16; ++k) {
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(16u * bytes) : "memory");
+    __syncwarp();
+    if (lane < 16) {
+      const size_t r = (size_t)fmix32((uint32_t)(warp * 7919u + (k * 16 + lane) * 104729u + 17u)) % nrows;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + (size_t)lane * row_doubles);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(src + r * row_doubles), "r"(bytes), "r"(bar_s)
+                   : "memory");
+    }
+    unsigned ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(ok)
+          : "r"(bar_s), "r"((unsigned)(k & 1))
+          : "memory");
+    }
+  }
+  if (buf[lane] == 123.456) *sink = buf[lane];
+}
+
 int fail(Comm& c, const std::string& msg) {
   c.err = msg;
   return 1;
@@ -141,6 +201,8 @@ int comm_init(Comm& c, const char* id128, int rank, int nranks, int mode, int64_
   NCK(c, api.CommInitRank(&comm, nranks, id, rank));
   c.nccl = comm;
   CCK(c, cudaMalloc(&c.ranges, table_cap * MAX_SPLITS * sizeof(int2)));
+  CCK(c, cudaMalloc(&c.done, sizeof(unsigned)));
+  CCK(c, cudaMemsetAsync(c.done, 0, sizeof(unsigned), st));
   CCK(c, cudaMemsetAsync(c.flags, 0, MAX_RANKS * sizeof(unsigned), st));
   CCK(c, cudaStreamSynchronize(st));
   return 0;
@@ -183,12 +245,62 @@ int comm_import(Comm& c, const char* blobs) {
   return 0;
 }
 
+// GB/s of reading `peer`'s coords buffer (peer == own rank: local HBM) with pattern `what`:
+// 0 streaming 16-byte loads, 1 random whole rows with 16-byte loads, 2 random whole rows with TMA bulk copies
+int comm_probe(Comm& c, int peer, int what, int row_doubles, cudaStream_t st, double* gbs) {
+  if (peer < 0 || peer >= c.nranks) return fail(c, "comm_probe: bad peer");
+  if (peer != c.rank && !c.imported) return fail(c, "comm_probe: peer memory not imported");
+  const double* src = peer == c.rank ? c.coords : static_cast<const double*>(c.peer_base[peer]);
+  const size_t total = (size_t)c.N * c.D;  // doubles
+  double* sink = nullptr;
+  CCK(c, cudaMalloc(&sink, 8));
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double bytes = 0;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, st);
+    if (what == 0) {
+      probe_stream_kernel<<<sms * 8, 512, 0, st>>>(reinterpret_cast<const double2*>(src), total / 2, sink);
+      bytes = (double)total * 8;
+    } else {
+      const size_t nrows = total / row_doubles;
+      const int rows_per_warp = 64, warps = sms * 16;
+      if (what == 1) {
+        probe_rows_kernel<<<sms * 2, 256, 0, st>>>(reinterpret_cast<const double2*>(src), nrows, row_doubles / 2,
+                                                  rows_per_warp, sink);
+      } else {
+        const size_t smem = (size_t)8 * 16 * row_doubles * sizeof(double) + 8 * sizeof(uint64_t);
+        cudaFuncSetAttribute(probe_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        probe_bulk_kernel<<<sms * 2, 256, smem, st>>>(src, nrows, row_doubles, rows_per_warp, sink);
+      }
+      bytes = (double)warps * rows_per_warp * row_doubles * 8;
+    }
+    cudaEventRecord(e1, st);
+    CCK(c, cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  CCK(c, cudaGetLastError());
+  *gbs = bytes / (best * 1e-3) / 1e9;
+  return 0;
+}
+
 void comm_destroy(Comm& c) {
   for (int r = 0; r < MAX_RANKS; ++r)
     if (c.peer_base[r]) cudaIpcCloseMemHandle(c.peer_base[r]);
   cudaFree(c.peer_coords_dev);
   cudaFree(c.peer_flags_dev);
   cudaFree(c.ranges);
+  cudaFree(c.done);
   if (c.nccl) nccl_api().CommDestroy(static_cast<ncclComm_t>(c.nccl));
   c = Comm();
 }
@@ -217,6 +329,19 @@ static int p2p_barrier(Comm& c, cudaStream_t st, int* status, uint64_t& launches
   CCK(c, cudaGetLastError());
   ++launches;
   return 0;
+}
+
+bool comm_fuse_barrier(Comm& c, HalfStepArgs& a) {
+  if (c.nranks == 1 || c.mode != EB_COMM_P2P || !c.imported) return false;
+  a.p2p_peer_flags = c.peer_flags_dev;
+  a.p2p_my_flags = c.flags;
+  a.p2p_done = c.done;
+  a.p2p_rank = c.rank;
+  a.p2p_nranks = c.nranks;
+  a.p2p_wait = c.epoch;        // everybody has finished the previous barrier event
+  a.p2p_signal = c.epoch + 1;  // ... and this kernel's completion is the next one
+  c.epoch += 1;
+  return true;
 }
 
 int comm_begin(Comm& c, cudaStream_t st, int* status, uint64_t& launches) {

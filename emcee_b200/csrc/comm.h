@@ -32,6 +32,7 @@ struct Comm {
   const double** peer_coords_dev = nullptr;  // device array [nranks]
   unsigned** peer_flags_dev = nullptr;       // device array [nranks]
   unsigned epoch = 0;
+  unsigned* done = nullptr;  // CTA-completion counter for the kernel-fused barrier
   bool imported = false;
   std::string err;
 };
@@ -42,12 +43,16 @@ int comm_init(Comm& c, const char* id128, int rank, int nranks, int mode, int64_
 int comm_export(Comm& c, char* blob);
 int comm_import(Comm& c, const char* blobs);
 void comm_destroy(Comm& c);
+int comm_probe(Comm& c, int peer, int what, int row_doubles, cudaStream_t st, double* gbs);
 // peer pointers / ownership for the kernels
 void comm_fill_args(const Comm& c, HalfStepArgs& a);
 // [i_lo, i_hi): the active ranks of this split owned by this rank (device resident when nranks > 1)
 void comm_active_range(const Comm& c, HalfStepArgs& a, size_t step_in_chunk);
 // P2P: all ranks rendezvous before the first split of a call
 int comm_begin(Comm& c, cudaStream_t st, int* status, uint64_t& launches);
+// P2P + dense_dmma: the barrier rides inside the half-step kernel (wait at its start, signal from
+// its last CTA); fills the p2p_* fields and advances the epoch.  Returns false if not applicable.
+bool comm_fuse_barrier(Comm& c, HalfStepArgs& a);
 // make the rows updated in this split visible to every rank
 int comm_after_split(Comm& c, cudaStream_t st, int* status, uint64_t& launches);
 // end of a stepping call: replicate log_prob / accept mask / counters (and coords in P2P mode)

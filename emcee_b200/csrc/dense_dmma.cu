@@ -242,6 +242,25 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
       Prep cur{}, nxt{};
       if (tile0 < ntiles) cur = prep(tile0, h == 0);
       if (h == 0) {
+        if (a.p2p_peer_flags != nullptr) {
+          // multi-GPU: no peer may still be reading (or not yet have written) what this half-step touches
+          bool ok = true;
+          if (lane < a.p2p_nranks && lane != a.p2p_rank) {
+            const volatile unsigned* f = a.p2p_my_flags + lane;
+            const long long t0 = clock64();
+            while ((int)(*f - a.p2p_wait) < 0) {
+              __nanosleep(64);
+              if (clock64() - t0 > 20000000000ll) {
+                atomicOr(a.status, FLAG_COMM_TIMEOUT);
+                ok = false;
+                break;
+              }
+            }
+          }
+          __threadfence_system();
+          asm volatile("fence.proxy.async;" ::: "memory");
+          if (!__all_sync(0xffffffffu, ok)) return;
+        }
         // launch start: get the first rows moving before anything else
         if (tile0 < ntiles) issue(cur, (int)(k & 1u), false);
         if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, true);
@@ -393,6 +412,20 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
       __threadfence();
       asm volatile("bar.sync 1, %0;" ::"r"(32 * DMMA_CONSUMERS) : "memory");
       if (tid == 0) grid_arrive(gbar);
+    }
+  }
+  if (a.p2p_peer_flags != nullptr) {
+    // multi-GPU: the last CTA of this rank to finish tells every peer that this half-step is done here
+    __threadfence_system();
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * DMMA_CONSUMERS) : "memory");
+    if (tid == 0) {
+      const unsigned prev = atomicAdd(a.p2p_done, 1u);
+      if (prev == gridDim.x - 1) {
+        *a.p2p_done = 0;  // re-armed for the next launch (stream order: nobody else touches it now)
+        __threadfence_system();
+        for (int r = 0; r < a.p2p_nranks; ++r)
+          if (r != a.p2p_rank) atomicExch_system(a.p2p_peer_flags[r] + a.p2p_rank, a.p2p_signal);
+      }
     }
   }
 }

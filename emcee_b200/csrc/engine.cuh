@@ -46,6 +46,13 @@ struct HalfStepArgs {
   const int32_t* order;      // [N] walker ids grouped by set, ascending inside a set
   const double* const* peer_coords;  // P2P mode: [nranks] peer-mapped coords (or null)
   int64_t rows_per_rank;     // P2P mode: owner(w) = w / rows_per_rank
+  // P2P mode, barrier fused into the kernel (dense_dmma): producers wait until every peer has
+  // published p2p_wait before touching the state; the last CTA to finish publishes p2p_signal
+  unsigned* const* p2p_peer_flags;  // [nranks] peer-mapped flag arrays (null: no fused barrier)
+  const unsigned* p2p_my_flags;     // [nranks] this rank's flag array (written by the peers)
+  unsigned* p2p_done;               // CTA-completion counter of this rank
+  int p2p_rank, p2p_nranks;
+  unsigned p2p_wait, p2p_signal;
   int64_t N;
   int D;
   int split;

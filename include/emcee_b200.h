@@ -190,6 +190,11 @@ int eb_comm_init(eb_ctx* ctx, const char id[EB_COMM_ID_BYTES], int rank, int nra
 int eb_comm_export(eb_ctx* ctx, char blob[EB_IPC_BLOB_BYTES]);
 int eb_comm_import(eb_ctx* ctx, const char* blobs /* nranks * EB_IPC_BLOB_BYTES */);
 
+/* measurement: GB/s of reading rank `peer`'s walker array (own rank = local HBM) with
+ * what = 0 streaming 16-byte loads, 1 random whole rows (16-byte loads), 2 random whole rows
+ * through TMA bulk copies (the dense_dmma producers' pattern). */
+int eb_comm_probe(eb_ctx* ctx, int peer, int what, double* gbs);
+
 #ifdef __cplusplus
 }
 #endif
