@@ -57,6 +57,29 @@ def launches(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, dst, key):
+    """profiles/traffic.json: DRAM bytes (read + write) per launch of the captured kernel"""
+    import json
+    import os
+
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = []
+    for r in rows[2:]:
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(m)
+            tot += float(r[i].replace(",", "")) * scale[units[i]]
+        vals.append(tot)
+    t = json.load(open(dst)) if os.path.exists(dst) else {}
+    t[key] = sum(vals) / len(vals)
+    t[key + "_source"] = os.path.basename(src) + " (ncu --set full, cold L2: every launch re-reads its walkers from HBM)"
+    json.dump(t, open(dst, "w"), indent=1)
+    print(t)
+
+
 def full(src, dst):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -75,4 +98,7 @@ def full(src, dst):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
