@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   if (tid == 0) {
     mbar_init(barL, 1);
     for (int c = 0; c < DMMA_CONSUMERS; ++c) {
-      mbar_init(barFull + c, 2);  // two arrivals per tile: partner-row batch, own-row batch
+      mbar_init(barFull + c, 1);
       mbar_init(barReady + c, 1);
       mbar_init(barFree + c, 1);
     }
@@ -178,12 +178,8 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   const int64_t tstride = (int64_t)gridDim.x * DMMA_CONSUMERS;
   const int64_t tile0 = (int64_t)blockIdx.x + (int64_t)gridDim.x * pair;  // SM-major deal
   double* slot = sSlots + (size_t)pair * SL::slot_doubles;
-  // The slot has two halves of 8 rows.  Tile k lands its partner rows (later its proposal) in half
-  // X_k = (k + 1) & 1 and its own rows in the other one: the half that held the own rows of tile k
-  // is free as soon as the proposal is formed, so the partner rows of tile k + 1 -- the ones that
-  // may come over NVLink -- are requested a whole tensor-pipe phase before the slot is released.
-  double* myHalf0 = slot + (size_t)g * RS + 2 * t;  // this lane's 16-byte chunks of row g
-  double* myHalf1 = myHalf0 + 8 * RS;
+  double* myS = slot + (size_t)g * RS + 2 * t;  // this lane's 16-byte chunks of row g
+  double* myC = myS + 8 * RS;                   // partner row, later the proposal
   TileMeta* meta = sMeta + 2 * pair;
   unsigned k = 0;  // tiles this pair has handled so far in the launch (mbarrier phase counter)
 
@@ -222,24 +218,18 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
         p.lp_old = with_lp ? a.logp[p.w] : 0.0;
         return p;
       };
-      // partner rows of a tile -> slot half hx (8 TMA bulk copies; may cross NVLink)
-      auto issue_partner = [&](const Prep& p, int hx) {
-        if (lane == 0) mbar_arrive_expect_tx(barFull + pair, 8u * D * (unsigned)sizeof(double));
+      // publish the meta record and launch the 16 row copies of one tile into the landing slot
+      auto issue = [&](Prep& p, int par, bool load_lp) {
+        if (lane == 0) mbar_arrive_expect_tx(barFull + pair, 16u * D * (unsigned)sizeof(double));
         __syncwarp();
-        if (lane < 8) {
-          const int64_t wr = (int64_t)p.wp;
-          const double* base = a.peer_coords != nullptr ? a.peer_coords[wr / a.rows_per_rank] : a.coords;
-          bulk_g2s(slot + (size_t)hx * 8 * RS + (size_t)row * RS, base + (size_t)wr * D,
+        if (lane < 16) {
+          const bool partner = lane >= 8;
+          const int64_t wr = partner ? (int64_t)p.wp : (int64_t)p.w;
+          const double* base =
+              (partner && a.peer_coords != nullptr) ? a.peer_coords[wr / a.rows_per_rank] : a.coords;
+          bulk_g2s(slot + (size_t)(partner ? 8 : 0) * RS + (size_t)row * RS, base + (size_t)wr * D,
                    (unsigned)(D * sizeof(double)), barFull + pair);
         }
-      };
-      // own rows -> the other half, and the meta record of the tile
-      auto issue_self = [&](Prep& p, int hx, int par, bool load_lp) {
-        if (lane == 0) mbar_arrive_expect_tx(barFull + pair, 8u * D * (unsigned)sizeof(double));
-        __syncwarp();
-        if (lane < 8)
-          bulk_g2s(slot + (size_t)(hx ^ 1) * 8 * RS + (size_t)row * RS, a.coords + (size_t)p.w * D,
-                   (unsigned)(D * sizeof(double)), barFull + pair);
         if (load_lp) p.lp_old = a.logp[p.w];  // behind the row copies: off the post-barrier critical path
         TileMeta* m = meta + par;
         if (lane < 8) {
@@ -272,10 +262,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
           if (!__all_sync(0xffffffffu, ok)) return;
         }
         // launch start: get the first rows moving before anything else
-        if (tile0 < ntiles) {
-          issue_partner(cur, (int)((k + 1) & 1u));
-          issue_self(cur, (int)((k + 1) & 1u), (int)(k & 1u), false);
-        }
+        if (tile0 < ntiles) issue(cur, (int)(k & 1u), false);
         if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, true);
       } else {
         if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, false);
@@ -287,37 +274,31 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
         if (tile0 < ntiles) {
           // the slot was released by the consumer at the end of the previous half-step's last tile
           if (k > 0) mbar_wait(barFree + pair, (k - 1) & 1u);
-          issue_partner(cur, (int)((k + 1) & 1u));
-          issue_self(cur, (int)((k + 1) & 1u), (int)(k & 1u), true);
+          issue(cur, (int)(k & 1u), true);
         }
       }
       for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++k) {
         // ---- rows of this tile have landed: form the proposal over the partner rows
-        const int hx = (int)((k + 1) & 1u);
-        double* pc = hx ? myHalf1 : myHalf0;        // partner rows -> proposal
-        const double* ps = hx ? myHalf0 : myHalf1;  // own rows
         const double zz = __shfl_sync(0xffffffffu, cur.zz, g);
         mbar_wait(barFull + pair, k & 1u);
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
-          const double2 s2 = *reinterpret_cast<const double2*>(ps + 8 * j);
-          const double2 c2 = *reinterpret_cast<const double2*>(pc + 8 * j);
+          const double2 s2 = *reinterpret_cast<const double2*>(myS + 8 * j);
+          const double2 c2 = *reinterpret_cast<const double2*>(myC + 8 * j);
           // stretch.py:33  q = c - (c - s) * zz, each op rounded once (no FMA contraction)
           double2 q2;
           q2.x = __dsub_rn(c2.x, __dmul_rn(__dsub_rn(c2.x, s2.x), zz));
           q2.y = __dsub_rn(c2.y, __dmul_rn(__dsub_rn(c2.y, s2.y), zz));
-          *reinterpret_cast<double2*>(pc + 8 * j) = q2;
+          *reinterpret_cast<double2*>(myC + 8 * j) = q2;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(barReady + pair);
+        // ---- as soon as the consumer has the proposal in registers, refill the slot
         if (tile + tstride < ntiles) {
           cur = nxt;
-          // the half that held the own rows is free NOW: start the (possibly remote) partner rows of
-          // the next tile a whole tensor-pipe phase before the consumer releases the other half
-          issue_partner(cur, hx ^ 1);
-          if (tile + 2 * tstride < ntiles) nxt = prep(tile + 2 * tstride, true);
           mbar_wait(barFree + pair, k & 1u);
-          issue_self(cur, hx ^ 1, (int)((k + 1) & 1u), h > 0 && tile == tile0);
+          issue(cur, (int)((k + 1) & 1u), h > 0 && tile == tile0);
+          if (tile + 2 * tstride < ntiles) nxt = prep(tile + 2 * tstride, true);
         }
       }
     }
@@ -344,11 +325,10 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
       }
       mbar_wait(barReady + pair, k & 1u);
       if (tlk) tlk[2] = clock64() - t_entry;
-      const double* pq = ((k + 1) & 1u) ? myHalf1 : myHalf0;  // half X_k holds the proposal
       double q[2 * KB];
 #pragma unroll
       for (int j = 0; j < KB; ++j) {
-        const double2 q2 = *reinterpret_cast<const double2*>(pq + 8 * j);
+        const double2 q2 = *reinterpret_cast<const double2*>(myC + 8 * j);
         q[2 * j + 0] = q2.x;
         q[2 * j + 1] = q2.y;
       }
