@@ -71,6 +71,7 @@ struct eb_ctx {
   const char* last_kernel = "none";
   bool allow_dmma = true;
   bool fused_last = false;  // the last dense_dmma launch carried the P2P barrier itself
+  int dmma_stagger = 1;
   int dmma_group = 1;  // half-steps per persistent dense_dmma launch (1: a launch per half-step)
 
   Comm comm;  // multi-GPU (comm.h)
@@ -487,6 +488,7 @@ void fill_base_args(eb_ctx* c, const eb_move& mv, HalfStepArgs& a) {
       a.p0 = mv.p0;  // gammas
   }
   a.timeline = c->timeline;
+  a.dmma_stagger = c->dmma_stagger;
   comm_fill_args(c->comm, a);
 }
 
@@ -831,6 +833,10 @@ int eb_set_option(eb_ctx* c, const char* name, int64_t value) {
   }
   if (!strcmp(name, "l2_flush")) {
     c->l2_flush = value != 0;
+    return EB_OK;
+  }
+  if (!strcmp(name, "dmma_stagger")) {
+    c->dmma_stagger = value != 0;
     return EB_OK;
   }
   if (!strcmp(name, "dmma_group")) {

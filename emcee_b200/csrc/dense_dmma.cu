@@ -261,8 +261,14 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
           asm volatile("fence.proxy.async;" ::: "memory");
           if (!__all_sync(0xffffffffu, ok)) return;
         }
-        // launch start: get the first rows moving before anything else
-        if (tile0 < ntiles) issue(cur, (int)(k & 1u), false);
+        // launch start: get the first rows moving before anything else.  All 8 pairs asking at once is a
+        // 19 MB burst (148 SMs x 8 slots x 16 KB) during which nobody computes; with the stagger the second
+        // pair of each sub-partition asks only when the first pair's rows are in, so one consumer per
+        // sub-partition starts after half the burst.
+        if (tile0 < ntiles) {
+          if (a.dmma_stagger && pair >= DMMA_CONSUMERS / 2) mbar_wait(barFull + pair - DMMA_CONSUMERS / 2, 0);
+          issue(cur, (int)(k & 1u), false);
+        }
         if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, true);
       } else {
         if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, false);

@@ -53,6 +53,7 @@ struct HalfStepArgs {
   unsigned* p2p_done;               // CTA-completion counter of this rank
   int p2p_rank, p2p_nranks;
   unsigned p2p_wait, p2p_signal;
+  int dmma_stagger;  // dense_dmma: pairs 4..7 request their first tile only when pairs 0..3's rows have landed
   int64_t N;
   int D;
   int split;

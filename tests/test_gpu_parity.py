@@ -134,6 +134,11 @@ CASES = [
     ("gauss_dense", 4096, 128, [(rb.Stretch(), 1.0)], 12),
     ("gauss_dense", 2048, 64, [(rb.Stretch(a=2.5, nsplits=3), 1.0)], 8),
     ("gauss_dense", 1000, 24, [(rb.Stretch(randomize_split=False), 1.0)], 8),
+    # dense_dmma with partial tiles (active counts not multiples of 8), three splits, fewer tiles than SMs
+    ("gauss_dense", 1004, 32, [(rb.Stretch(), 1.0)], 10),
+    ("gauss_dense", 301, 48, [(rb.Stretch(nsplits=3), 1.0)], 10),
+    ("gauss_dense", 100, 16, [(rb.Stretch(a=1.5), 1.0)], 10),
+    ("gauss_dense", 20000, 96, [(rb.Stretch(), 1.0)], 6),
     ("gauss_iso", 512, 37, [(rb.Stretch(), 1.0)], 10),
     ("ring", 16384, 32, [(rb.Stretch(), 1.0)], 8),
     ("rosenbrock", 2048, 256, [(rb.DE(), 0.8), (rb.Snooker(), 0.2)], 12),
