@@ -5,10 +5,10 @@ that the hot path covers."""
 
 __version__ = "0.1.0"
 
-from . import models, moves
+from . import autocorr, models, moves
 from .backend import Backend
 from .ensemble import EnsembleSampler, walkers_independent
 from .model import Model
 from .state import State
 
-__all__ = ["EnsembleSampler", "walkers_independent", "State", "Model", "Backend", "moves", "models", "__version__"]
+__all__ = ["EnsembleSampler", "walkers_independent", "State", "Model", "Backend", "moves", "models", "autocorr", "__version__"]

@@ -100,10 +100,13 @@ class Backend(object):
         k = self.iteration - 1
         return State(self.chain[k], log_prob=self.log_prob[k], blobs=None, random_state=self.random_state)
 
-    def get_autocorr_time(self, **kwargs):
-        raise NotImplementedError(
-            "autocorrelation analysis is outside the walker-update hot path (DESIGN.md, 'next')"
-        )
+    def get_autocorr_time(self, discard=0, thin=1, **kwargs):
+        """Integrated autocorrelation time per parameter, in steps
+        (``backend.py:130-150``)."""
+        from . import autocorr
+
+        x = self.get_chain(discard=discard, thin=thin)
+        return thin * autocorr.integrated_time(x, **kwargs)
 
     def __enter__(self):
         return self

@@ -443,11 +443,14 @@ cudaError_t launch_t(const HalfStepArgs& a, const HalfDesc& d0, const HalfDesc* 
   const size_t smem = SmemLayout<KB>::total_bytes;
   const bool has_mean = a.model.s0 != 0.0;  // set by eb_model_set when mu != 0
   auto kern = has_mean ? half_step_dense_dmma_kernel<KB, true> : half_step_dense_dmma_kernel<KB, false>;
-  static bool configured[2] = {false, false};
-  if (!configured[has_mean]) {
+  // the opt-in to > 48 KB of dynamic shared memory is per device: remember where it has been done
+  static bool configured[2][64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[has_mean][dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[has_mean] = true;
+    if (dev >= 0 && dev < 64) configured[has_mean][dev] = true;
   }
   *grid_out = 0;
   if (max_count <= 0 || nhalf <= 0) return cudaSuccess;

@@ -106,6 +106,7 @@ class EnsembleSampler(object):
         self.log_prob_fn = log_prob_fn
         self.params_are_named = False
 
+        self._device = int(device)
         self._engine = _lib.Engine(self.nwalkers, self.ndim, _seed_from_numpy() if seed is None else seed,
                                    device=device)
         self._engine.set_model(log_prob_fn.kind, log_prob_fn.device_params(self.ndim))
@@ -152,7 +153,30 @@ class EnsembleSampler(object):
         self.backend.reset(self.nwalkers, self.ndim)
 
     def __getstate__(self):
-        raise NotImplementedError("a sampler that owns GPU memory cannot be pickled")
+        """Picklable like the reference (``ensemble.py:251-256``, pinned by
+        ``tests/unit/test_sampler.py:225-234``): the GPU engine is dropped and
+        rebuilt on unpickling from the model, the Philox ``(seed, step)`` and
+        the device index; the walker state travels through ``_previous_state``
+        / the backend as it does in the reference."""
+        d = dict(self.__dict__)
+        d["_saved_rng"] = self._engine.get_rng()
+        d["_saved_pinned"] = self._pinned is not None
+        for k in ("_engine", "_random", "_pinned"):
+            d.pop(k, None)
+        d["pool"] = None
+        return d
+
+    def __setstate__(self, d):
+        seed, step = d.pop("_saved_rng")
+        pinned = d.pop("_saved_pinned")
+        self.__dict__.update(d)
+        self._engine = _lib.Engine(self.nwalkers, self.ndim, seed, device=self._device)
+        self._engine.set_model(self.log_prob_fn.kind, self.log_prob_fn.device_params(self.ndim))
+        self._engine.set_rng(seed, step)
+        self._random = DeviceRandom(self._engine)
+        self._pinned = None
+        if pinned:
+            self._pinned = (_lib.pinned_empty((self.nwalkers, self.ndim)), _lib.pinned_empty((self.nwalkers,)))
 
     # ------------------------------------------------------------- the driver
     def _schedule(self):
@@ -178,8 +202,16 @@ class EnsembleSampler(object):
         live :class:`State` every ``thin_by`` steps."""
         if log_prob0 is not None or rstate0 is not None or blobs0 is not None:
             raise NotImplementedError("log_prob0/rstate0/blobs0 are deprecated in the reference; pass a State")
+        pbar = None
         if progress:
-            raise NotImplementedError("progress bars are outside the hot path")
+            # the reference wraps tqdm (pbar.py:33-60); one tick per yielded state here
+            try:
+                import tqdm
+
+                total = None if iterations is None else iterations
+                pbar = tqdm.tqdm(total=total, **(progress_kwargs or {}))
+            except ImportError:
+                pbar = None
         if iterations is None and store:
             raise ValueError("'store' must be False when 'iterations' is None")
 
@@ -245,6 +277,9 @@ class EnsembleSampler(object):
                 else:
                     eng.step(sched, total, want_accepted=False)
             refresh()
+            if pbar is not None:
+                pbar.update(iterations)
+                pbar.close()
             if iterations > 0:
                 yield state
             return
@@ -267,7 +302,11 @@ class EnsembleSampler(object):
                 if last_is_checkpoint:
                     self.backend.save_step(state, accepted)
             i += yield_step
+            if pbar is not None:
+                pbar.update(1)
             yield state
+        if pbar is not None:
+            pbar.close()
 
     def run_mcmc(self, initial_state, nsteps, **kwargs):
         """Iterate :func:`sample` for ``nsteps`` iterations and return the last

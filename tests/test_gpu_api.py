@@ -86,6 +86,30 @@ def test_input_not_overwritten_and_resume():
     assert np.array_equal(s.get_chain(), s2.get_chain())
 
 
+def test_pickle_roundtrip():
+    # tests/unit/test_sampler.py:225-234
+    import pickle
+
+    s = make(seed=5)
+    p0 = np.random.default_rng(8).standard_normal((32, 3))
+    s.run_mcmc(p0, 10)
+    s2 = pickle.loads(pickle.dumps(s))
+    assert np.array_equal(s2.get_chain(), s.get_chain())
+    assert s2.random_state == s.random_state
+    a = s.run_mcmc(None, 5)
+    b = s2.run_mcmc(None, 5)
+    assert np.array_equal(a.coords, b.coords) and np.array_equal(s.get_chain(), s2.get_chain())
+
+
+def test_progress_bar_smoke():
+    s = make(seed=6)
+    p0 = np.random.default_rng(9).standard_normal((32, 3))
+    s.run_mcmc(p0, 5, progress=True, progress_kwargs={"disable": True})
+    for _ in s.sample(p0, iterations=3, progress=True, progress_kwargs={"disable": True}):
+        pass
+    assert s.iteration == 8
+
+
 def test_thin_by_equivalence():
     # tests/unit/test_sampler.py:152-194
     p0 = np.random.default_rng(5).standard_normal((32, 3))
