@@ -70,6 +70,7 @@ struct eb_ctx {
   uint64_t last_launches = 0;
   const char* last_kernel = "none";
   bool allow_dmma = true;
+  bool allow_tma = false;  // flipped on once validated on hardware
   bool fused_last = false;  // the last dense_dmma launch carried the P2P barrier itself
   int dmma_stagger = 1;
   int dmma_group = 1;  // half-steps per persistent dense_dmma launch (1: a launch per half-step)
@@ -528,8 +529,14 @@ int launch_step_generic(eb_ctx* c, const eb_move& mv, uint64_t step, const int32
       ++k;
     }
     comm_active_range(c->comm, a, step_in_chunk);  // i_lo / i_hi for this rank
-    CK(c, launch_half_step_generic(mv.kind, a, c->st));
-    c->last_kernel = "generic";
+    bool used_tma = false;
+    if (c->allow_tma && !c->debug) CK(c, launch_half_step_tma(mv.kind, a, c->sm_count, c->st, &used_tma));
+    if (used_tma) {
+      c->last_kernel = "tma_rows";
+    } else {
+      CK(c, launch_half_step_generic(mv.kind, a, c->st));
+      c->last_kernel = "generic";
+    }
     ++launches;
     c->tap_count = a.a_count;
     if (comm_after_split(c->comm, c->st, c->status_dev, launches)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
@@ -842,6 +849,10 @@ int eb_set_option(eb_ctx* c, const char* name, int64_t value) {
   if (!strcmp(name, "dmma_group")) {
     if (value < 1) FAIL(c, EB_ERR_INVALID, "dmma_group must be >= 1");
     c->dmma_group = (int)std::min<int64_t>(value, 1 << 20);
+    return EB_OK;
+  }
+  if (!strcmp(name, "tma_rows")) {
+    c->allow_tma = value != 0;
     return EB_OK;
   }
   if (!strcmp(name, "dense_dmma")) {

@@ -32,6 +32,7 @@
 #include <math.h>
 
 #include "engine.cuh"
+#include "tma.cuh"
 
 namespace eb {
 
@@ -45,46 +46,6 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
-}
-
-// ---- mbarrier / TMA bulk copy primitives (PTX ISA 8.x, sm_90+) ----------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: a lost partner traps the kernel (an error the host reports) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000ll) __trap();  // ~4 s
-  }
-}
-// global -> shared bulk copy (TMA, SASS UBLKCP); completion is counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
 }
 
 __host__ __device__ constexpr int packed_blocks(int KB) { return KB * (KB + 1); }  // 2 * KB(KB+1)/2
@@ -470,18 +431,8 @@ cudaError_t launch_t(const HalfStepArgs& a, const HalfDesc& d0, const HalfDesc* 
 
 }  // namespace
 
-bool dense_dmma_supported(int D) {
-  switch (D) {
-    case 16:
-    case 32:
-    case 48:
-    case 64:
-    case 96:
-    case 128:
-      return true;
-  }
-  return false;
-}
+// any ndim that is a multiple of 8 up to 128 (the proposal tile lives in D/4 registers per lane)
+bool dense_dmma_supported(int D) { return D >= 8 && D <= 128 && D % 8 == 0; }
 
 size_t dense_dmma_factor_doubles(int D) { return (size_t)packed_blocks(D / 8) * 32; }
 
@@ -506,23 +457,30 @@ void dense_dmma_pack_factor(const double* L, int D, double* packed) {
 }
 
 cudaError_t launch_dense_dmma(const HalfStepArgs& a, const HalfDesc& d0, const HalfDesc* descs_dev, int nhalf,
-                              int max_count,
-                              unsigned long long* gbar, unsigned long long gbar_base, int sm_count, int* grid_out,
-                              cudaStream_t st) {
+                              int max_count, unsigned long long* gbar, unsigned long long gbar_base, int sm_count,
+                              int* grid_out, cudaStream_t st) {
+#define EB_DMMA_CASE(KB) \
+  case 8 * KB:           \
+    return launch_t<KB>(a, d0, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
   switch (a.D) {
-    case 16:
-      return launch_t<2>(a, d0, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
-    case 32:
-      return launch_t<4>(a, d0, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
-    case 48:
-      return launch_t<6>(a, d0, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
-    case 64:
-      return launch_t<8>(a, d0, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
-    case 96:
-      return launch_t<12>(a, d0, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
-    case 128:
-      return launch_t<16>(a, d0, descs_dev, nhalf, max_count, gbar, gbar_base, sm_count, grid_out, st);
+    EB_DMMA_CASE(1)
+    EB_DMMA_CASE(2)
+    EB_DMMA_CASE(3)
+    EB_DMMA_CASE(4)
+    EB_DMMA_CASE(5)
+    EB_DMMA_CASE(6)
+    EB_DMMA_CASE(7)
+    EB_DMMA_CASE(8)
+    EB_DMMA_CASE(9)
+    EB_DMMA_CASE(10)
+    EB_DMMA_CASE(11)
+    EB_DMMA_CASE(12)
+    EB_DMMA_CASE(13)
+    EB_DMMA_CASE(14)
+    EB_DMMA_CASE(15)
+    EB_DMMA_CASE(16)
   }
+#undef EB_DMMA_CASE
   return cudaErrorNotSupported;
 }
 

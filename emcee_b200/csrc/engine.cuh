@@ -80,6 +80,8 @@ cudaError_t launch_split_tables(int32_t* order, const StepInfo* info_dev, int ns
                                 uint64_t seed, uint64_t step0, int64_t w_lo, int64_t w_hi, int2* ranges,
                                 cudaStream_t st);
 cudaError_t launch_half_step_generic(int move_kind, const HalfStepArgs& a, cudaStream_t st);
+// TMA row-gather variant for the HBM-bound models (tma_rows.cu); *used == false: not applicable, use the generic one
+cudaError_t launch_half_step_tma(int move_kind, const HalfStepArgs& a, int sm_count, cudaStream_t st, bool* used);
 cudaError_t launch_logprob_generic(const ModelDev& m, const double* x, int64_t rows, int D, double* out,
                                    int* status, cudaStream_t st);
 // specialised: stretch + dense Gaussian on FP64 tensor cores (DMMA).  Returns

@@ -1,0 +1,295 @@
+// Fused half-step for the HBM-bound models (gauss_iso, ring, rosenbrock), any red-blue move,
+// with the row gathers on the TMA engine.
+//
+// Reference semantics: identical to half_step_generic_kernel (kernels.cu): moves/red_blue.py:82-104,
+// stretch.py:26-33, de.py:40-64, de_snooker.py:31-46, ensemble.py:476-479,550-551, move.py:29-34.
+//
+// Why a second kernel: these moves are pure row gathers -- a walker-step touches its own row
+// and 1-3 random partner rows and does O(D) flops -- so the roof is HBM and what matters is how
+// the rows travel.  Measured on this pool (eb_comm_probe, profiles/r01_nvlink_probe.txt): random
+// 256-byte rows move at 1.3 TB/s with 16-byte loads and 4.3 TB/s as TMA bulk copies (0.28 vs
+// 0.65 TB/s from a peer GPU).  So here every row is ONE cp.async.bulk into shared memory
+// (completion on an mbarrier), accepted rows leave as ONE bulk store, and each warp runs a
+// two-stage pipeline: the rows of tile k+1 are in flight while tile k is computed.
+//
+// Layout of a stage: [NR][R][D + G] doubles -- NR rows per walker (own + partners), R walkers
+// per tile, G = 32 / R lanes per walker; the G-double pad staggers consecutive walkers' rows
+// across the banks so a warp-wide access costs the minimum two wavefronts.
+#include <math.h>
+
+#include "engine.cuh"
+#include "rowops.cuh"
+#include "tma.cuh"
+
+namespace eb {
+
+namespace {
+
+constexpr int TMA_THREADS = 256;
+constexpr int TMA_WARPS = TMA_THREADS / 32;
+
+template <int MOVE>
+struct RowsPerWalker {
+  static constexpr int value = MOVE == EB_MOVE_STRETCH ? 2 : (MOVE == EB_MOVE_DE ? 3 : 4);
+};
+
+// what one lane group keeps about its walker of a tile
+struct WalkerMeta {
+  int32_t w;       // active walker id, < 0 for the padding rows of a partial tile
+  int32_t pw[3];   // partner walker ids (stretch: [0]; DE: p0, p1; snooker: z, z1, z2)
+  double scalar;   // stretch: zz | DE: gamma
+  double u_acc;    // accept uniform
+};
+
+template <int MOVE, int MODEL>
+__global__ void __launch_bounds__(TMA_THREADS, 1) half_step_tma_kernel(const HalfStepArgs a, const int R) {
+  constexpr int NR = RowsPerWalker<MOVE>::value;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int D = a.D;
+  const int G = 32 / R;           // lanes per walker
+  const int RS = D + G;           // padded row stride (doubles)
+  const int stage_doubles = NR * R * RS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = lane / G, g = lane % G;
+  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+
+  double* wbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * stage_doubles;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TMA_WARPS * 2 * stage_doubles * sizeof(double)) + 2 * warp;
+  if (lane == 0) {
+    mbar_init(bars + 0, 1);
+    mbar_init(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int i_lo = a.range ? a.range->x : a.i_lo;
+  const int i_hi = a.range ? a.range->y : a.i_hi;
+  const int64_t ntiles = ((int64_t)i_hi - i_lo + R - 1) / R;
+  const int64_t tstride = (int64_t)gridDim.x * TMA_WARPS;
+  const int64_t Nc = a.N - a.a_count;
+  const unsigned row_bytes = (unsigned)(D * sizeof(double));
+
+  // ---- draws and index lookups of this lane group's walker in one tile -------------------
+  auto prep = [&](int64_t tile) -> WalkerMeta {
+    WalkerMeta m;
+    int64_t i = (int64_t)i_lo + tile * R + grp;
+    const bool valid = i < i_hi;
+    if (!valid) i = (int64_t)i_hi - 1;
+    const u32x4 A = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_PROP_A, (uint32_t)i);
+    m.pw[0] = m.pw[1] = m.pw[2] = 0;
+    m.scalar = 0.0;
+    if (MOVE == EB_MOVE_STRETCH) {
+      const double t = __dadd_rn(__dmul_rn(__dsub_rn(a.p0, 1.0), u53(A.x, A.y)), 1.0);  // stretch.py:30
+      m.scalar = __ddiv_rn(__dmul_rn(t, t), a.p0);
+      const int64_t r = (int64_t)bounded64(A.z, A.w, (uint64_t)Nc);  // stretch.py:32
+      m.pw[0] = __ldg(a.order + (r < a.a_start ? r : r + a.a_count));
+    } else if (MOVE == EB_MOVE_DE) {
+      const uint64_t mm = bounded64(A.x, A.y, (uint64_t)Nc * (uint64_t)(Nc - 1));  // de.py:49
+      uint64_t r0, r1;
+      de_pair_decode(mm, (uint64_t)Nc, r0, r1);  // de.py:67-77
+      m.pw[0] = __ldg(a.order + ((int64_t)r0 < a.a_start ? (int64_t)r0 : (int64_t)r0 + a.a_count));
+      m.pw[1] = __ldg(a.order + ((int64_t)r1 < a.a_start ? (int64_t)r1 : (int64_t)r1 + a.a_count));
+      const u32x4 B = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_PROP_B, (uint32_t)i);
+      const double n = sqrt(-2.0 * log(1.0 - u53(B.x, B.y))) * cos(6.283185307179586 * u53(B.z, B.w));
+      m.scalar = __dmul_rn(a.p0, __dadd_rn(1.0, __dmul_rn(a.p1, n)));  // de.py:56
+    } else {
+      const u32x4 B = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_PROP_B, (uint32_t)i);
+      int32_t cw[3];
+      cw[0] = __ldg(a.order + a.c_start[0] + (int64_t)bounded64(A.x, A.y, (uint64_t)a.c_count[0]));  // de_snooker.py:38
+      cw[1] = __ldg(a.order + a.c_start[1] + (int64_t)bounded64(A.z, A.w, (uint64_t)a.c_count[1]));
+      cw[2] = __ldg(a.order + a.c_start[2] + (int64_t)bounded64(B.x, B.y, (uint64_t)a.c_count[2]));
+      const int p = (int)bounded64(B.z, B.w, 6);  // de_snooker.py:39: one of the 6 row orders
+      const int i0 = p >> 1;
+      const int rest0 = (i0 == 0) ? 1 : 0, rest1 = (i0 == 2) ? 1 : 2;
+      const int i1 = (p & 1) ? rest1 : rest0, i2 = (p & 1) ? rest0 : rest1;
+      m.pw[0] = i0 == 0 ? cw[0] : (i0 == 1 ? cw[1] : cw[2]);
+      m.pw[1] = i1 == 0 ? cw[0] : (i1 == 1 ? cw[1] : cw[2]);
+      m.pw[2] = i2 == 0 ? cw[0] : (i2 == 1 ? cw[1] : cw[2]);
+    }
+    const int32_t w = __ldg(a.order + a.a_start + i);
+    m.w = valid ? w : -(w + 1);  // keep the id (its rows are still fetched), flag it as padding
+    const u32x4 U = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_ACCEPT, (uint32_t)i);
+    m.u_acc = u53(U.x, U.y);
+    return m;
+  };
+  // ---- launch the NR * R row copies of a tile into a stage ----------------------------------
+  auto issue = [&](const WalkerMeta& m, int stage) {
+    double* buf = wbuf + (size_t)stage * stage_doubles;
+    if (lane == 0) mbar_arrive_expect_tx(bars + stage, (unsigned)(NR * R) * row_bytes);
+    __syncwarp();
+    // copy c (< NR*R <= 32) is row j = c / R of walker r = c % R; its ids live in lane r*G
+    const int c = lane, j = c / R, r = c % R;
+    const int wself = m.w >= 0 ? m.w : -(m.w + 1);
+    const int src_self = __shfl_sync(0xffffffffu, wself, (r * G) & 31);
+    const int src_p0 = __shfl_sync(0xffffffffu, m.pw[0], (r * G) & 31);
+    const int src_p1 = __shfl_sync(0xffffffffu, m.pw[1], (r * G) & 31);
+    const int src_p2 = __shfl_sync(0xffffffffu, m.pw[2], (r * G) & 31);
+    if (c < NR * R) {
+      const int64_t wr = j == 0 ? src_self : (j == 1 ? src_p0 : (j == 2 ? src_p1 : src_p2));
+      const double* src = (j == 0) ? a.coords + (size_t)wr * D : row_ptr(a, wr);
+      bulk_g2s(buf + ((size_t)j * R + r) * RS, src, row_bytes, bars + stage);
+    }
+  };
+
+  int64_t tile = (int64_t)blockIdx.x + (int64_t)gridDim.x * warp;  // SM-major deal, as dense_dmma
+  WalkerMeta cur{}, nxt{};
+  if (tile < ntiles) {
+    cur = prep(tile);
+    issue(cur, 0);
+  }
+  unsigned k = 0;
+  for (; tile < ntiles; tile += tstride, ++k) {
+    const int stage = (int)(k & 1u);
+    double* buf = wbuf + (size_t)stage * stage_doubles;
+    const bool has_next = tile + tstride < ntiles;
+    if (has_next) {
+      nxt = prep(tile + tstride);
+      bulk_wait_read();  // the accepted rows of tile k-1 have left the other stage
+      __syncwarp();
+      issue(nxt, stage ^ 1);
+    }
+    mbar_wait(bars + stage, (k >> 1) & 1u);
+
+    double* s = buf + ((size_t)0 * R + grp) * RS;  // own row, overwritten by the proposal
+    const bool valid = cur.w >= 0;
+    const int64_t w = valid ? cur.w : -(cur.w + 1);
+    double factor = 0.0;
+
+    if (MOVE == EB_MOVE_STRETCH) {
+      const double* c = buf + ((size_t)1 * R + grp) * RS;
+      const double zz = cur.scalar;
+      for (int e = g; e < D; e += G) {
+        const double sv = s[e], cv = c[e];
+        // stretch.py:33  q = c - (c - s) * zz   (each op rounded once, no FMA contraction)
+        const double v = __dsub_rn(cv, __dmul_rn(__dsub_rn(cv, sv), zz));
+        s[e] = v;
+        if (!isfinite(v)) flag_nonfinite(v, a.status);
+      }
+      factor = __dmul_rn((double)D - 1.0, log(zz));  // stretch.py:31
+    } else if (MOVE == EB_MOVE_DE) {
+      const double* c0 = buf + ((size_t)1 * R + grp) * RS;
+      const double* c1 = buf + ((size_t)2 * R + grp) * RS;
+      const double gamma = cur.scalar;
+      for (int e = g; e < D; e += G) {
+        // de.py:53,62  q = s + gamma * (c[p1] - c[p0])
+        const double v = __dadd_rn(s[e], __dmul_rn(gamma, __dsub_rn(c1[e], c0[e])));
+        s[e] = v;
+        if (!isfinite(v)) flag_nonfinite(v, a.status);
+      }
+    } else {
+      const double* z = buf + ((size_t)1 * R + grp) * RS;
+      double* z1 = buf + ((size_t)2 * R + grp) * RS;  // becomes u
+      const double* z2 = buf + ((size_t)3 * R + grp) * RS;
+      double n2 = 0.0;
+      for (int e = g; e < D; e += G) {
+        const double d = __dsub_rn(s[e], z[e]);  // de_snooker.py:41
+        n2 = fma(d, d, n2);
+      }
+      const double norm = sqrt(group_sum(n2, G, mask));  // de_snooker.py:42
+      double d1 = 0.0, d2 = 0.0;
+      for (int e = g; e < D; e += G) {
+        const double u = __ddiv_rn(__dsub_rn(s[e], z[e]), norm);  // de_snooker.py:43
+        d1 = fma(u, z1[e], d1);
+        d2 = fma(u, z2[e], d2);
+        z1[e] = u;
+      }
+      d1 = group_sum(d1, G, mask);
+      d2 = group_sum(d2, G, mask);
+      const double dd = __dsub_rn(d1, d2);
+      double m2 = 0.0;
+      for (int e = g; e < D; e += G) {
+        // de_snooker.py:44  q = s + u * gammas * (u.z1 - u.z2)
+        const double v = __dadd_rn(s[e], __dmul_rn(__dmul_rn(z1[e], a.p0), dd));
+        s[e] = v;
+        if (!isfinite(v)) flag_nonfinite(v, a.status);
+        const double dq = __dsub_rn(v, z[e]);
+        m2 = fma(dq, dq, m2);
+      }
+      const double qn = sqrt(group_sum(m2, G, mask));
+      factor = __dmul_rn((double)D - 1.0, __dsub_rn(log(qn), log(norm)));  // de_snooker.py:45-46
+    }
+    __syncwarp(mask);
+
+    // red_blue.py:93 -> ensemble.py:458-553
+    const double lp_new = model_logprob<MODEL>(s, nullptr, D, g, G, mask, a.model);
+    if (isnan(lp_new) && g == 0) atomicOr(a.status, FLAG_NAN_LOGPROB);
+    // red_blue.py:96-101
+    const double lnpdiff = __dsub_rn(__dadd_rn(factor, lp_new), a.logp[w]);
+    const bool acc = valid && (lnpdiff > log(cur.u_acc));
+    // red_blue.py:103-104 -> move.py:29-34: one bulk store per accepted row
+    fence_async_smem();
+    __syncwarp();
+    if (g == 0) {
+      if (acc) {
+        bulk_s2g(a.coords + (size_t)w * D, s, row_bytes);
+        a.logp[w] = lp_new;
+        atomicAdd(a.nacc + w, 1ull);
+      }
+      if (valid) a.accepted[w] = acc ? 1 : 0;
+    }
+    bulk_commit();
+    cur = nxt;
+  }
+  bulk_wait_read();  // shared memory must outlive the stores that read it
+}
+
+template <int MOVE, int MODEL>
+cudaError_t launch_tma_t(const HalfStepArgs& a, int sm_count, cudaStream_t st, bool* used) {
+  constexpr int NR = RowsPerWalker<MOVE>::value;
+  *used = false;
+  const int D = a.D;
+  if (D % 2 != 0) return cudaSuccess;  // rows must be multiples of 16 bytes for bulk copies
+  // walkers per tile: the largest power of two with NR*R <= 32 copies per stage and <= 24 KB per warp
+  int R = 16;
+  auto warp_bytes = [&](int r) { return (size_t)2 * NR * r * (D + 32 / r) * sizeof(double); };
+  while (R >= 1 && (NR * R > 32 || warp_bytes(R) > 24 * 1024)) R >>= 1;
+  if (R < 1) return cudaSuccess;  // rows too long for the staging budget: generic kernel
+  const size_t smem = (size_t)TMA_WARPS * warp_bytes(R) + (size_t)TMA_WARPS * 2 * sizeof(uint64_t);
+  const int64_t count = (int64_t)a.i_hi - a.i_lo;
+  if (count <= 0) {
+    *used = true;
+    return cudaSuccess;
+  }
+  auto kern = half_step_tma_kernel<MOVE, MODEL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int64_t ntiles = (count + R - 1) / R;
+  const int64_t want = (ntiles + TMA_WARPS - 1) / TMA_WARPS;
+  const int grid = (int)(want < sm_count ? want : sm_count);
+  kern<<<grid, TMA_THREADS, smem, st>>>(a, R);
+  *used = true;
+  return cudaGetLastError();
+}
+
+template <int MOVE>
+cudaError_t launch_tma_m(const HalfStepArgs& a, int sm_count, cudaStream_t st, bool* used) {
+  switch (a.model.kind) {
+    case EB_MODEL_GAUSS_ISO:
+      return launch_tma_t<MOVE, EB_MODEL_GAUSS_ISO>(a, sm_count, st, used);
+    case EB_MODEL_ROSENBROCK:
+      return launch_tma_t<MOVE, EB_MODEL_ROSENBROCK>(a, sm_count, st, used);
+    case EB_MODEL_RING:
+      return launch_tma_t<MOVE, EB_MODEL_RING>(a, sm_count, st, used);
+  }
+  *used = false;  // dense Gaussian outside the DMMA envelope: CUDA-core generic kernel
+  return cudaSuccess;
+}
+
+}  // namespace
+
+// Tries the TMA row-gather kernel; *used tells whether it took the half-step (otherwise the
+// caller falls back to half_step_generic_kernel).
+cudaError_t launch_half_step_tma(int move_kind, const HalfStepArgs& a, int sm_count, cudaStream_t st, bool* used) {
+  switch (move_kind) {
+    case EB_MOVE_STRETCH:
+      return launch_tma_m<EB_MOVE_STRETCH>(a, sm_count, st, used);
+    case EB_MOVE_DE:
+      return launch_tma_m<EB_MOVE_DE>(a, sm_count, st, used);
+    case EB_MOVE_SNOOKER:
+      return launch_tma_m<EB_MOVE_SNOOKER>(a, sm_count, st, used);
+  }
+  *used = false;
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace eb

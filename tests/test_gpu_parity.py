@@ -147,6 +147,24 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("D", [8, 24, 40, 56, 72, 80, 88, 104, 112, 120])
+def test_dense_dmma_every_width(D):
+    """the tensor-core kernel is instantiated for every ndim = 8k <= 128 (with and without a mean)"""
+    N = 2 * D + 8 * (D % 5) + 42  # active counts that are not multiples of 8
+    target, p0 = T.make_config("gauss_dense", N, D)
+    mean = np.linspace(-0.5, 0.5, D) if D % 16 == 8 else None
+    tgt = T.GaussDense(target.icov, mean)
+    o = rb.OracleSampler(N, D, tgt, [(rb.Stretch(), 1.0)], seed=D)
+    o.set_state(p0)
+    s = emcee_b200.EnsembleSampler(N, D, emcee_b200.models.GaussianDense(target.icov, mean), seed=D)
+    last = s.run_mcmc(p0, 6, store=False, skip_initial_state_check=True)
+    o.run(6)
+    assert s._engine.last_kernel_name() == "dense_dmma"
+    assert np.array_equal(last.coords, o.coords)
+    np.testing.assert_allclose(last.log_prob, o.log_prob, rtol=1e-11, atol=1e-11)
+    assert np.array_equal(s._engine.naccepted(), o.naccepted.astype(np.uint64))
+
+
 @pytest.mark.parametrize("name,N,D,omoves,nsteps", CASES)
 def test_against_oracle(name, N, D, omoves, nsteps):
     target, p0 = T.make_config(name, N, D)
