@@ -265,6 +265,8 @@ def run_b200(args, dist):
         eng.set_option("dmma_group", args.dmma_group)
     if args.no_tma_rows:
         eng.set_option("tma_rows", 0)
+    if args.tma_rows:
+        eng.set_option("tma_rows", 1)
     if args.no_stagger:
         eng.set_option("dmma_stagger", 0)
     sched = sampler._schedule()
@@ -390,6 +392,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-microbench", action="store_true",
                     help="do not launch the fp64 peak micro-benchmarks (for ncu launch lists); use the recorded peak")
+    ap.add_argument("--tma-rows", action="store_true", help="force the tma_rows kernel on")
     ap.add_argument("--no-tma-rows", action="store_true", help="HBM-bound models: use the generic kernel instead of tma_rows")
     ap.add_argument("--no-stagger", action="store_true", help="dense_dmma: all pairs request their first tile at once")
     ap.add_argument("--dmma-group", type=int, default=0, help="half-steps per persistent dense_dmma launch (0: library default)")

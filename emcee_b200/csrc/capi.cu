@@ -2,6 +2,7 @@
 // state / model transfer, error mapping.  No torch, no CPU fallback.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -70,7 +71,7 @@ struct eb_ctx {
   uint64_t last_launches = 0;
   const char* last_kernel = "none";
   bool allow_dmma = true;
-  bool allow_tma = false;  // flipped on once validated on hardware
+  bool allow_tma = true;
   bool fused_last = false;  // the last dense_dmma launch carried the P2P barrier itself
   int dmma_stagger = 1;
   int dmma_group = 1;  // half-steps per persistent dense_dmma launch (1: a launch per half-step)
@@ -159,6 +160,7 @@ int eb_create(int device, int64_t nwalkers, int64_t ndim, uint64_t seed, eb_ctx*
   c->N = nwalkers;
   c->D = (int)ndim;
   c->seed = seed;
+  if (const char* e = getenv("EMCEE_B200_TMA_ROWS")) c->allow_tma = atoi(e) != 0;  // developer override
   auto fail = [&](const char* what, cudaError_t err) {
     g_create_err = std::string("eb_create: ") + what + ": " + cudaGetErrorString(err);
     eb_destroy(c);

@@ -25,8 +25,7 @@ namespace eb {
 
 namespace {
 
-constexpr int TMA_THREADS = 256;
-constexpr int TMA_WARPS = TMA_THREADS / 32;
+constexpr int TMA_MAX_THREADS = 512;  // 16 warps when the rows are short enough, else 8
 
 template <int MOVE>
 struct RowsPerWalker {
@@ -42,7 +41,7 @@ struct WalkerMeta {
 };
 
 template <int MOVE, int MODEL>
-__global__ void __launch_bounds__(TMA_THREADS, 1) half_step_tma_kernel(const HalfStepArgs a, const int R) {
+__global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const HalfStepArgs a, const int R) {
   constexpr int NR = RowsPerWalker<MOVE>::value;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D;
@@ -50,11 +49,12 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) half_step_tma_kernel(const Hal
   const int RS = D + G;           // padded row stride (doubles)
   const int stage_doubles = NR * R * RS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = blockDim.x >> 5;
   const int grp = lane / G, g = lane % G;
   const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
 
   double* wbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * stage_doubles;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TMA_WARPS * 2 * stage_doubles * sizeof(double)) + 2 * warp;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nwarps * 2 * stage_doubles * sizeof(double)) + 2 * warp;
   if (lane == 0) {
     mbar_init(bars + 0, 1);
     mbar_init(bars + 1, 1);
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) half_step_tma_kernel(const Hal
   const int i_lo = a.range ? a.range->x : a.i_lo;
   const int i_hi = a.range ? a.range->y : a.i_hi;
   const int64_t ntiles = ((int64_t)i_hi - i_lo + R - 1) / R;
-  const int64_t tstride = (int64_t)gridDim.x * TMA_WARPS;
+  const int64_t tstride = (int64_t)gridDim.x * nwarps;
   const int64_t Nc = a.N - a.a_count;
   const unsigned row_bytes = (unsigned)(D * sizeof(double));
 
@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) half_step_tma_kernel(const Hal
     bulk_commit();
     cur = nxt;
   }
-  bulk_wait_read();  // shared memory must outlive the stores that read it
+  // every accepted row has left shared memory AND reached global memory before the warp retires
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 template <int MOVE, int MODEL>
@@ -239,12 +240,23 @@ cudaError_t launch_tma_t(const HalfStepArgs& a, int sm_count, cudaStream_t st, b
   *used = false;
   const int D = a.D;
   if (D % 2 != 0) return cudaSuccess;  // rows must be multiples of 16 bytes for bulk copies
-  // walkers per tile: the largest power of two with NR*R <= 32 copies per stage and <= 24 KB per warp
-  int R = 16;
+  // Latency is hidden by warps: 16 per SM, each with a 12 KB share of shared memory for its two
+  // stages; walkers per tile R = the largest power of two with NR*R <= 32 copies per stage that
+  // fits.  Measured (profiles/r01_tma_rows_ab.txt): with R >= 2 this kernel beats the generic one
+  // (ring 262144x32 +9 %, iso 65536x128 +18 %); for rows so long that only one walker per tile
+  // (or only 8 warps) fits -- e.g. 256-D DE/snooker -- the generic kernel is 23 % faster, so
+  // those shapes stay there.
   auto warp_bytes = [&](int r) { return (size_t)2 * NR * r * (D + 32 / r) * sizeof(double); };
-  while (R >= 1 && (NR * R > 32 || warp_bytes(R) > 24 * 1024)) R >>= 1;
-  if (R < 1) return cudaSuccess;  // rows too long for the staging budget: generic kernel
-  const size_t smem = (size_t)TMA_WARPS * warp_bytes(R) + (size_t)TMA_WARPS * 2 * sizeof(uint64_t);
+  const int nwarps = 16;
+  const size_t budget = (size_t)192 * 1024 / nwarps;
+  int R = 0;
+  for (int r = 16; r >= 2; r >>= 1)
+    if (NR * r <= 32 && warp_bytes(r) <= budget) {
+      R = r;
+      break;
+    }
+  if (R == 0) return cudaSuccess;  // generic kernel
+  const size_t smem = (size_t)nwarps * warp_bytes(R) + (size_t)nwarps * 2 * sizeof(uint64_t);
   const int64_t count = (int64_t)a.i_hi - a.i_lo;
   if (count <= 0) {
     *used = true;
@@ -254,9 +266,9 @@ cudaError_t launch_tma_t(const HalfStepArgs& a, int sm_count, cudaStream_t st, b
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t ntiles = (count + R - 1) / R;
-  const int64_t want = (ntiles + TMA_WARPS - 1) / TMA_WARPS;
+  const int64_t want = (ntiles + nwarps - 1) / nwarps;
   const int grid = (int)(want < sm_count ? want : sm_count);
-  kern<<<grid, TMA_THREADS, smem, st>>>(a, R);
+  kern<<<grid, 32 * nwarps, smem, st>>>(a, R);
   *used = true;
   return cudaGetLastError();
 }
