@@ -326,6 +326,13 @@ int eb_model_set(eb_ctx* c, int kind, const double* params, size_t nparams) {
 }
 
 // ---- log-prob ----------------------------------------------------------------
+// rows of x -> out with the kernel that matches the stepping path of the model
+static cudaError_t launch_logprob(eb_ctx* c, const double* x, int64_t rows, double* out) {
+  if (c->allow_dmma && c->model.kind == EB_MODEL_GAUSS_DENSE && c->model.chol != nullptr)
+    return launch_logprob_dense_dmma(c->model, c->D, x, rows, out, c->status_dev, c->sm_count, c->st);
+  return launch_logprob_generic(c->model, x, rows, c->D, out, c->status_dev, c->st);
+}
+
 static int ensure_scratch(eb_ctx* c, size_t rows) {
   if (rows <= c->scratch_rows) return EB_OK;
   CK(c, cudaStreamSynchronize(c->st));
@@ -350,7 +357,7 @@ int eb_compute_log_prob(eb_ctx* c, const double* coords, size_t m, double* out) 
   if (rc) return rc;
   CK(c, cudaMemcpyAsync(c->scratch_x, coords, m * (size_t)c->D * sizeof(double), cudaMemcpyHostToDevice,
                         c->st));
-  CK(c, launch_logprob_generic(c->model, c->scratch_x, (int64_t)m, c->D, c->scratch_lp, c->status_dev, c->st));
+  CK(c, launch_logprob(c, c->scratch_x, (int64_t)m, c->scratch_lp));
   CK(c, cudaMemcpyAsync(out, c->scratch_lp, m * sizeof(double), cudaMemcpyDeviceToHost, c->st));
   return fetch_status(c);
 }
@@ -372,7 +379,7 @@ int eb_set_state(eb_ctx* c, const double* coords, const double* log_prob) {
     CK(c, cudaMemcpyAsync(c->logp, log_prob, (size_t)c->N * sizeof(double), cudaMemcpyHostToDevice, c->st));
     CK(c, cudaStreamSynchronize(c->st));
   } else {
-    CK(c, launch_logprob_generic(c->model, c->coords, c->N, c->D, c->logp, c->status_dev, c->st));
+    CK(c, launch_logprob(c, c->coords, c->N, c->logp));
     int rc = fetch_status(c);
     if (rc) return rc;
   }

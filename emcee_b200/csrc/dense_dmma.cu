@@ -74,6 +74,48 @@ struct SmemLayout {
   static constexpr size_t total_bytes = off_bars_bytes + (1 + 3 * DMMA_CONSUMERS) * sizeof(uint64_t);
 };
 
+// The tensor-pipe block of the stand-alone log-prob kernel: the same statements, in the same order, as
+// the block inlined in the half-step kernel's consumer (kept inline there: its register allocation is
+// tuned to the last register), so both produce bit-identical values for the same row: this lane's partial sum over its two columns of
+// |L^T (q - mu)|^2 for the 8 rows of the warp's tile; q holds the lane's A fragments.
+template <int KB, bool HAS_MEAN>
+__device__ __forceinline__ double tile_sumsq(const double (&q)[2 * KB], const double* sL, const double* sMu, int lane,
+                                             int t) {
+  double rs = 0.0;
+  const double* bptr = sL + 2 * lane;  // one 16-byte load feeds the two k-halves of a block pair
+#pragma unroll
+  for (int nb0 = 0; nb0 < KB; nb0 += NI) {
+    double c[NI][2][2];
+#pragma unroll
+    for (int n = 0; n < NI; ++n) c[n][0][0] = c[n][0][1] = c[n][1][0] = c[n][1][1] = 0.0;
+#pragma unroll
+    for (int j = nb0; j < KB; ++j) {
+      double x0 = q[2 * j + 0], x1 = q[2 * j + 1];
+      if (HAS_MEAN) {
+        const double2 m2 = *reinterpret_cast<const double2*>(sMu + 8 * j + 2 * t);
+        x0 -= m2.x;
+        x1 -= m2.y;
+      }
+#pragma unroll
+      for (int n = 0; n < NI; ++n) {
+        if (nb0 + n < KB && j >= nb0 + n) {
+          const double2 b2 = *reinterpret_cast<const double2*>(bptr);
+          dmma884(c[n][0][0], c[n][0][1], x0, b2.x);
+          dmma884(c[n][1][0], c[n][1][1], x1, b2.y);
+          bptr += 64;
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NI; ++n) {
+      const double y0 = c[n][0][0] + c[n][1][0], y1 = c[n][0][1] + c[n][1][1];
+      rs = fma(y0, y0, rs);
+      rs = fma(y1, y1, rs);
+    }
+  }
+  return rs;
+}
+
 // grid-wide barrier between consecutive half-steps of one persistent launch: the
 // consumers of every CTA publish "my writes of half-step h are out" on a global
 // counter; producers wait for all CTAs before they read state for half-step h+1.
@@ -397,6 +439,84 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   }
 }
 
+// ===========================================================================
+// stand-alone log-probability of dense-Gaussian rows on the tensor pipe
+// (EnsembleSampler.compute_log_prob and the initial state, ensemble.py:350-358,458-553)
+// ===========================================================================
+template <int KB, bool HAS_MEAN>
+__global__ void __launch_bounds__(256) logprob_dense_dmma_kernel(const ModelDev m, const double* __restrict__ x,
+                                                                 const int64_t rows, double* __restrict__ out,
+                                                                 int* status) {
+  constexpr int D = 8 * KB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sL = reinterpret_cast<double*>(smem_raw);
+  double* sMu = sL + (size_t)packed_blocks(KB) * 32;
+  uint64_t* barL = reinterpret_cast<uint64_t*>(sMu + D);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  if (tid == 0) {
+    mbar_init(barL, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (HAS_MEAN)
+    for (int k = tid; k < D; k += blockDim.x) sMu[k] = m.params[k];
+  __syncthreads();
+  if (tid == 0) {
+    constexpr unsigned bytes = (unsigned)((size_t)packed_blocks(KB) * 32 * sizeof(double));
+    mbar_arrive_expect_tx(barL, bytes);
+    bulk_g2s(sL, m.chol, bytes, barL);
+  }
+  const int64_t ntiles = (rows + 7) >> 3;
+  bool waited = false;
+  for (int64_t tile = (int64_t)blockIdx.x * 8 + warp; tile < ntiles; tile += (int64_t)gridDim.x * 8) {
+    int64_t r = tile * 8 + g;
+    const bool valid = r < rows;
+    if (!valid) r = rows - 1;
+    const double* src = x + (size_t)r * D + 2 * t;
+    double q[2 * KB];
+    bool any_inf = false, any_nan = false;
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(src + 8 * j));
+      q[2 * j + 0] = v.x;
+      q[2 * j + 1] = v.y;
+      any_inf |= isinf(v.x) | isinf(v.y);
+      any_nan |= isnan(v.x) | isnan(v.y);
+    }
+    if (valid && any_inf) atomicOr(status, FLAG_INF_PARAM);  // ensemble.py:476-477
+    if (valid && any_nan) atomicOr(status, FLAG_NAN_PARAM);  // ensemble.py:478-479
+    if (!waited) {
+      mbar_wait(barL, 0);
+      waited = true;
+    }
+    double rs = tile_sumsq<KB, HAS_MEAN>(q, sL, sMu, lane, t);
+    rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+    rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+    const double lp = -0.5 * rs;
+    if (valid && t == 0) {
+      out[r] = lp;
+      if (isnan(lp)) atomicOr(status, FLAG_NAN_LOGPROB);  // ensemble.py:550-551
+    }
+  }
+}
+
+template <int KB>
+cudaError_t launch_lp_t(const ModelDev& m, const double* x, int64_t rows, double* out, int* status, int sm_count,
+                        cudaStream_t st) {
+  const size_t smem = ((size_t)packed_blocks(KB) * 32 + 8 * KB) * sizeof(double) + sizeof(uint64_t);
+  const bool has_mean = m.s0 != 0.0;
+  auto kern = has_mean ? logprob_dense_dmma_kernel<KB, true> : logprob_dense_dmma_kernel<KB, false>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  if (rows <= 0) return cudaSuccess;
+  const int64_t want = (((rows + 7) >> 3) + 7) / 8;
+  const int grid = (int)(want < 2 * sm_count ? want : 2 * sm_count);
+  kern<<<grid, 256, smem, st>>>(m, x, rows, out, status);
+  return cudaGetLastError();
+}
+
 template <int KB>
 cudaError_t launch_t(const HalfStepArgs& a, const HalfDesc& d0, const HalfDesc* descs_dev, int nhalf, int max_count,
                      unsigned long long* gbar, unsigned long long gbar_base, int sm_count, int* grid_out,
@@ -454,6 +574,33 @@ void dense_dmma_pack_factor(const double* L, int D, double* packed) {
             packed[idx++] = L[(size_t)(8 * j + 2 * t + half) * D + (8 * nb + g)];
           }
       }
+}
+
+cudaError_t launch_logprob_dense_dmma(const ModelDev& m, int D, const double* x, int64_t rows, double* out,
+                                      int* status, int sm_count, cudaStream_t st) {
+#define EB_LP_CASE(KB) \
+  case 8 * KB:         \
+    return launch_lp_t<KB>(m, x, rows, out, status, sm_count, st);
+  switch (D) {
+    EB_LP_CASE(1)
+    EB_LP_CASE(2)
+    EB_LP_CASE(3)
+    EB_LP_CASE(4)
+    EB_LP_CASE(5)
+    EB_LP_CASE(6)
+    EB_LP_CASE(7)
+    EB_LP_CASE(8)
+    EB_LP_CASE(9)
+    EB_LP_CASE(10)
+    EB_LP_CASE(11)
+    EB_LP_CASE(12)
+    EB_LP_CASE(13)
+    EB_LP_CASE(14)
+    EB_LP_CASE(15)
+    EB_LP_CASE(16)
+  }
+#undef EB_LP_CASE
+  return cudaErrorNotSupported;
 }
 
 cudaError_t launch_dense_dmma(const HalfStepArgs& a, const HalfDesc& d0, const HalfDesc* descs_dev, int nhalf,

@@ -89,6 +89,9 @@ cudaError_t launch_logprob_generic(const ModelDev& m, const double* x, int64_t r
 bool dense_dmma_supported(int D);
 size_t dense_dmma_factor_doubles(int D);
 void dense_dmma_pack_factor(const double* L, int D, double* packed);  // host
+// log-probability of dense-Gaussian rows on the tensor pipe (same arithmetic as the half-step kernel)
+cudaError_t launch_logprob_dense_dmma(const ModelDev& m, int D, const double* x, int64_t rows, double* out,
+                                      int* status, int sm_count, cudaStream_t st);
 // one half-step of a persistent dense_dmma launch
 struct HalfDesc {
   uint64_t step;       // sampler step index (Philox counter)

@@ -56,6 +56,27 @@ def test_errors():
         s.run_mcmc(st, 1, skip_initial_state_check=True)
 
 
+def test_dense_log_prob_guards_and_consistency():
+    """the tensor-core log-prob kernel: reference guards, and bit-identical values to the stepping kernel"""
+    from oracle import targets as T
+
+    target, p0 = T.make_config("gauss_dense", 520, 64)
+    s = emcee_b200.EnsembleSampler(520, 64, models.GaussianDense(target.icov), seed=9)
+    lp, _ = s.compute_log_prob(p0)
+    np.testing.assert_allclose(lp, target(p0), rtol=1e-11, atol=1e-9)
+    assert np.array_equal(s.compute_log_prob(p0[:7])[0], lp[:7])  # partial tile, same arithmetic
+    bad = p0.copy()
+    bad[519, 63] = np.inf
+    with pytest.raises(ValueError, match="infinite"):
+        s.compute_log_prob(bad)
+    bad[519, 63] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        s.compute_log_prob(bad)
+    # after a run, the stored log_prob equals a fresh evaluation of the stored coordinates bit for bit
+    last = s.run_mcmc(p0, 12, store=False, skip_initial_state_check=True)
+    assert np.array_equal(s.compute_log_prob(last.coords)[0], last.log_prob)
+
+
 def test_live_dangerously_guard():
     # tests/unit/test_stretch.py:15-34 -- drives Move.propose through the Model boundary
     nwalkers, ndim = 4, 3
