@@ -43,6 +43,10 @@ struct eb_ctx {
   HalfDesc* descs_host = nullptr;  // pinned
   unsigned long long* gbar = nullptr;  // grid-barrier counter of the persistent dense_dmma kernel
   unsigned long long gbar_count = 0;   // arrivals issued so far
+  // split tables already on the device: steps [tbl_step0, tbl_step0 + tbl_n) of key tbl_seed, built with tbl_info
+  uint64_t tbl_seed = 0, tbl_step0 = 0;
+  size_t tbl_n = 0;
+  std::vector<StepInfo> tbl_info;
 
   double* scratch_x = nullptr;
   double* scratch_lp = nullptr;
@@ -611,13 +615,41 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
       const eb_move& mv = s.moves[pick[k]];
       c->info_host[k].nsplits = mv.nsplits;
       c->info_host[k].randomize = mv.randomize_split;
+    }
+    // Split tables depend only on (seed, step, nsplits, randomize): reuse the ones already on the
+    // device when they cover this chunk, else build them -- looking ahead with the same schedule, so
+    // a caller that steps one iteration per call pays for one table launch every 64 calls, not one each.
+    size_t off = 0, build = 0;
+    bool hit = c->tbl_n > 0 && c->tbl_seed == c->seed && c->step >= c->tbl_step0 &&
+               c->step + chunk <= c->tbl_step0 + c->tbl_n;
+    if (hit) {
+      off = (size_t)(c->step - c->tbl_step0);
+      for (size_t k = 0; k < chunk && hit; ++k)
+        hit = c->tbl_info[off + k].nsplits == c->info_host[k].nsplits &&
+              c->tbl_info[off + k].randomize == c->info_host[k].randomize;
+    }
+    if (!hit) {
+      off = 0;
+      build = std::min<size_t>(c->table_cap, std::max<size_t>(chunk, 64));
+      for (size_t k = chunk; k < build; ++k) {
+        const eb_move& mv = s.moves[choose_move(c, s, c->step + k)];
+        c->info_host[k].nsplits = mv.nsplits;
+        c->info_host[k].randomize = mv.randomize_split;
+      }
+      c->tbl_seed = c->seed;
+      c->tbl_step0 = c->step;
+      c->tbl_n = build;
+      c->tbl_info.assign(c->info_host, c->info_host + build);
+    }
+    for (size_t k = 0; k < chunk; ++k) {
+      const eb_move& mv = s.moves[pick[k]];
       if (dmma_eligible(c, mv)) {
         int start[MAX_SPLITS + 1];
         split_starts(c->N, mv.nsplits, start);
         for (int split = 0; split < mv.nsplits; ++split) {
           HalfDesc& d = c->descs_host[ndesc++];
           d.step = c->step + k;
-          d.order_step = (int32_t)k;
+          d.order_step = (int32_t)(off + k);
           d.split = split;
           d.a_start = start[split];
           d.a_count = start[split + 1] - start[split];
@@ -634,15 +666,17 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
         CK(c, cudaEventRecord(c->ev_pool[2 * (done + k)], c->st));
       }
       if (k == 0) {
-        // split tables (and dense_dmma descriptors) of the whole chunk, charged to its first step
-        CK(c, cudaMemcpyAsync(c->info_dev, c->info_host, chunk * sizeof(StepInfo), cudaMemcpyHostToDevice, c->st));
+        // dense_dmma descriptors of the chunk and, when needed, the split tables (charged to this step)
         if (ndesc)
           CK(c, cudaMemcpyAsync(c->descs_dev, c->descs_host, ndesc * sizeof(HalfDesc), cudaMemcpyHostToDevice, c->st));
-        const Comm& cm = c->comm;
-        CK(c, launch_split_tables(c->order, c->info_dev, (int)chunk, c->N, c->seed, c->step,
-                                  cm.rows_per_rank * cm.rank, cm.rows_per_rank * (cm.rank + 1),
-                                  cm.nranks > 1 ? cm.ranges : nullptr, c->st));
-        ++launches;
+        if (build) {
+          CK(c, cudaMemcpyAsync(c->info_dev, c->info_host, build * sizeof(StepInfo), cudaMemcpyHostToDevice, c->st));
+          const Comm& cm = c->comm;
+          CK(c, launch_split_tables(c->order, c->info_dev, (int)build, c->N, c->seed, c->step,
+                                    cm.rows_per_rank * cm.rank, cm.rows_per_rank * (cm.rank + 1),
+                                    cm.nranks > 1 ? cm.ranges : nullptr, c->st));
+          ++launches;
+        }
       }
       int rc;
       if (dmma_eligible(c, mv)) {
@@ -680,7 +714,7 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
           rc = flush_dmma(c, *grp_move, grp, launches);
           if (rc) return rc;
         }
-        rc = launch_step_generic(c, mv, c->step, c->order + k * (size_t)c->N, k, launches);
+        rc = launch_step_generic(c, mv, c->step, c->order + (off + k) * (size_t)c->N, off + k, launches);
         if (rc) return rc;
       }
       c->step += 1;
@@ -920,6 +954,7 @@ int eb_comm_id(char id[EB_COMM_ID_BYTES]) { return comm_unique_id(id) ? EB_ERR_C
 int eb_comm_init(eb_ctx* c, const char id[EB_COMM_ID_BYTES], int rank, int nranks, int mode) {
   if (!c) return EB_ERR_INVALID;
   CK(c, cudaSetDevice(c->device));
+  c->tbl_n = 0;  // the cached split tables carry the old ownership ranges
   unsigned* flags = reinterpret_cast<unsigned*>(c->coords + (size_t)c->N * c->D);
   if (comm_init(c->comm, id, rank, nranks, mode, c->N, c->D, c->coords, flags, c->table_cap, c->st))
     FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
