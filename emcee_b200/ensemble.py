@@ -152,6 +152,12 @@ class EnsembleSampler(object):
     def reset(self):
         self.backend.reset(self.nwalkers, self.ndim)
 
+    @property
+    def model(self):
+        """The 4-tuple the reference hands to ``move.propose`` (``ensemble.py:393-395``),
+        for callers that drive a move directly through the plugin boundary."""
+        return Model(self.log_prob_fn, self.compute_log_prob, map, self._random)
+
     def __getstate__(self):
         """Picklable like the reference (``ensemble.py:251-256``, pinned by
         ``tests/unit/test_sampler.py:225-234``): the GPU engine is dropped and

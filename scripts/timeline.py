@@ -1,11 +1,10 @@
 #!/usr/bin/env python
 """Consumer-warp timeline of the dense_dmma kernel (cycles), headline workload."""
 import sys
-import numpy as np
 sys.path.insert(0, ".")
 import bench
 import emcee_b200
-from emcee_b200 import models, moves
+from emcee_b200 import models
 
 w = bench.make_workload("gauss_dense", 65536, 128)
 s = emcee_b200.EnsembleSampler(65536, 128, models.GaussianDense(w["icov"]), seed=1)

@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """dense_dmma consumer timeline on rank 0 of a multi-GPU (P2P) run: torchrun ... scripts/timeline_mg.py"""
 import sys
-import numpy as np
 sys.path.insert(0, ".")
 import bench
 import emcee_b200

@@ -82,7 +82,7 @@ def test_live_dangerously_guard():
     nwalkers, ndim = 4, 3
     s = emcee_b200.EnsembleSampler(nwalkers, ndim, models.GaussianIso(), seed=1)
     coords = np.random.default_rng(3).standard_normal((nwalkers, ndim))
-    model = emcee_b200.Model(s.log_prob_fn, s.compute_log_prob, map, s._random)
+    model = s.model  # = emcee_b200.Model(s.log_prob_fn, s.compute_log_prob, map, s._random)
     state = emcee_b200.State(coords, log_prob=s.compute_log_prob(coords)[0])
     with pytest.raises(RuntimeError):
         moves.StretchMove().propose(model, state)
