@@ -79,7 +79,7 @@ __global__ void p2p_barrier_kernel(unsigned* const* peer_flags, volatile unsigne
     const long long t0 = clock64();
     while ((int)(my_flags[t] - epoch) < 0) {
       __nanosleep(64);
-      if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died; report instead of hanging the GPU
+      if (clock64() - t0 > 60000000000ll) {  // ~30 s: a peer died; report instead of hanging the GPU
         atomicOr(status, FLAG_COMM_TIMEOUT);
         break;
       }

@@ -127,7 +127,7 @@ __device__ __forceinline__ bool grid_wait(const unsigned long long* counter, uns
   const long long t0 = clock64();
   while (*reinterpret_cast<const volatile unsigned long long*>(counter) < target) {
     __nanosleep(32);
-    if (clock64() - t0 > 4000000000ll) {  // ~2 s: never hang the GPU on a lost CTA
+    if (clock64() - t0 > 60000000000ll) {  // ~30 s: never hang the GPU on a lost CTA
       atomicOr(status, FLAG_COMM_TIMEOUT);
       return false;
     }
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
             const long long t0 = clock64();
             while ((int)(*f - a.p2p_wait) < 0) {
               __nanosleep(64);
-              if (clock64() - t0 > 20000000000ll) {
+              if (clock64() - t0 > 60000000000ll) {  // ~30 s
                 atomicOr(a.status, FLAG_COMM_TIMEOUT);
                 ok = false;
                 break;
@@ -269,7 +269,9 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
         // pair of each sub-partition asks only when the first pair's rows are in, so one consumer per
         // sub-partition starts after half the burst.
         if (tile0 < ntiles) {
-          if (a.dmma_stagger && pair >= DMMA_CONSUMERS / 2) mbar_wait(barFull + pair - DMMA_CONSUMERS / 2, 0);
+          // (best effort, single GPU only: a bounded peek at the neighbour's barrier, never a dependency)
+          if (a.dmma_stagger && a.p2p_peer_flags == nullptr && pair >= DMMA_CONSUMERS / 2)
+            mbar_wait_for(barFull + pair - DMMA_CONSUMERS / 2, 0, 12000);
           issue(cur, (int)(k & 1u), false);
         }
         if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, true);

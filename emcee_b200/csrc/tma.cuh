@@ -28,12 +28,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: a lost partner traps the kernel (an error the host reports) instead of hanging the GPU
+// Bounded wait.  The bound is a last-resort guard against hanging the GPU on a lost partner (a trap is
+// an error the host reports); it must exceed every legitimate wait, including a producer that is itself
+// waiting for a peer GPU (30 s bound there), hence ~2 minutes.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000ll) __trap();  // ~4 s
+    if (clock64() - t0 > 240000000000ll) __trap();
+  }
+}
+// best-effort wait of at most `cycles`: for orderings that are optimisations, not dependencies
+__device__ __forceinline__ void mbar_wait_for(uint64_t* bar, unsigned parity, long long cycles) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > cycles) return;
   }
 }
 // global -> shared bulk copy (TMA, SASS UBLKCP); completion is counted in bytes on `bar`
