@@ -1,4 +1,11 @@
-"""Move protocol (reference: ``src/emcee/moves/move.py:8-45``)."""
+"""Move protocol of the device path.
+
+Reference interface: ``src/emcee/moves/move.py:8-45`` -- ``tune(state, accepted)`` and
+``update(old_state, new_state, accepted, subset=None)``.  On the device path both
+happen inside the fused half-step kernel (the accepted rows are written in place and
+red-blue moves have nothing to tune); the host versions below exist so that code written
+against the protocol -- e.g. a user-defined host move operating on ``State`` objects --
+keeps working."""
 
 import numpy as np
 
@@ -7,26 +14,20 @@ __all__ = ["Move"]
 
 class Move(object):
     def tune(self, state, accepted):
-        """No-op for every red-blue move (``move.py:9-10``)."""
-        pass
+        """Nothing to adapt for the red-blue moves."""
+        return None
 
     def update(self, old_state, new_state, accepted, subset=None):
-        """Masked scatter of accepted proposals into a host ``State``
-        (``move.py:12-45``).  The engine performs this update in the fused
-        half-step kernel; the method exists for host-side callers that build
-        their own moves on the ``State`` container."""
-        n = len(old_state.coords)
-        subset = np.ones(n, dtype=bool) if subset is None else subset
-        take = accepted[subset]
-        put = subset & accepted
-        old_state.coords[put] = new_state.coords[take]
-        old_state.log_prob[put] = new_state.log_prob[take]
+        """Scatter the accepted proposals of ``new_state`` (one row per member of
+        ``subset``, in ascending walker order) into ``old_state`` and return it."""
+        nwalkers = len(old_state.coords)
+        members = np.arange(nwalkers) if subset is None else np.flatnonzero(subset)
+        won = np.asarray(accepted, dtype=bool)[members]  # per proposal row
+        dst, src = members[won], np.flatnonzero(won)
+        old_state.coords[dst] = new_state.coords[src]
+        old_state.log_prob[dst] = new_state.log_prob[src]
         if new_state.blobs is not None:
             if old_state.blobs is None:
-                raise ValueError(
-                    "If you start sampling with a given log_prob, "
-                    "you also need to provide the current list of "
-                    "blobs at that position."
-                )
-            old_state.blobs[put] = new_state.blobs[take]
+                raise ValueError("the proposal carries blobs but the current state has none")
+            old_state.blobs[dst] = new_state.blobs[src]
         return old_state
