@@ -275,6 +275,8 @@ def run_b200(args, dist):
         eng.set_option("tma_rows", 1)
     if args.no_stagger:
         eng.set_option("dmma_stagger", 0)
+    if args.no_pdl:
+        eng.set_option("pdl", 0)
     sched = sampler._schedule()
 
     # ---- device-resident throughput (`value`) ------------------------------
@@ -401,6 +403,7 @@ def main():
     ap.add_argument("--tma-rows", action="store_true", help="force the tma_rows kernel on")
     ap.add_argument("--no-tma-rows", action="store_true", help="HBM-bound models: use the generic kernel instead of tma_rows")
     ap.add_argument("--no-stagger", action="store_true", help="dense_dmma: all pairs request their first tile at once")
+    ap.add_argument("--no-pdl", action="store_true", help="dense_dmma: plain stream-ordered launches instead of programmatic dependent launches")
     ap.add_argument("--dmma-group", type=int, default=0, help="half-steps per persistent dense_dmma launch (0: library default)")
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--cpu-nwalkers", type=int, default=65536)
@@ -413,7 +416,7 @@ def main():
     )
     from emcee_b200.dist import Rendezvous
 
-    dist = Rendezvous("gloo")
+    dist = Rendezvous()
     if dist.world != args.gpus and dist.world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, dist.world))
     try:

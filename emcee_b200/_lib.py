@@ -65,6 +65,8 @@ _SIGNATURES = {
     "eb_model_set": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_size_t]),
     "eb_set_state": (C.c_int, [C.c_void_p, _dp, _dp]),
     "eb_get_state": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "eb_owned_rows": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "eb_get_state_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _dp]),
     "eb_compute_log_prob": (C.c_int, [C.c_void_p, _dp, C.c_size_t, _dp]),
     "eb_set_rng": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
     "eb_get_rng": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -75,6 +77,8 @@ _SIGNATURES = {
     ),
     "eb_get_naccepted": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "eb_reset_counters": (C.c_int, [C.c_void_p]),
+    "eb_moments": (C.c_int, [C.c_void_p, _dp, _dp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "eb_walkers_gram": (C.c_int, [C.c_void_p, _dp, C.c_size_t, _dp, C.POINTER(C.c_int)]),
     "eb_last_step_timing": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_uint64)]),
     "eb_debug_taps": (
         C.c_int,
@@ -226,6 +230,40 @@ class Engine(object):
         assert lp.flags.c_contiguous and lp.dtype == np.float64 and lp.shape == (self.nwalkers,)
         self._check(lib().eb_get_state(self._h, _as_dp(coords), _as_dp(lp)))
         return coords, lp
+
+    def owned_rows(self):
+        """``(row0, nrows)`` of the walkers this engine updates (all of them on one GPU)."""
+        r0, n = C.c_int64(), C.c_int64()
+        self._check(lib().eb_owned_rows(self._h, C.byref(r0), C.byref(n)))
+        return int(r0.value), int(n.value)
+
+    def get_state_rows(self, row0, nrows, coords, log_prob):
+        """Device -> host copy of rows ``[row0, row0 + nrows)`` into the matching
+        row slices of the full-size host arrays ``coords`` / ``log_prob`` (not collective)."""
+        assert coords.flags.c_contiguous and coords.dtype == np.float64 and coords.shape == (self.nwalkers, self.ndim)
+        assert log_prob.flags.c_contiguous and log_prob.dtype == np.float64 and log_prob.shape == (self.nwalkers,)
+        c, lp = coords[row0 : row0 + nrows], log_prob[row0 : row0 + nrows]
+        self._check(lib().eb_get_state_rows(self._h, int(row0), int(nrows), _as_dp(c), _as_dp(lp)))
+        return coords, log_prob
+
+    def moments(self):
+        """``(mean[D], cov[D, D], count, naccepted_total)`` of the samples folded in so far
+        (option ``moments_every``); per rank on a sharded ensemble."""
+        mean = np.empty(self.ndim)
+        cov = np.empty((self.ndim, self.ndim))
+        n, na = C.c_uint64(), C.c_uint64()
+        self._check(lib().eb_moments(self._h, _as_dp(mean), _as_dp(cov), C.byref(n), C.byref(na)))
+        return mean, cov, int(n.value), int(na.value)
+
+    def walkers_gram(self, coords):
+        """``(gram[D, D], flags)`` of ``eb_walkers_gram`` for ``coords[rows, D]``."""
+        coords = _f64(coords)
+        if coords.ndim != 2 or coords.shape[1] != self.ndim:
+            raise ValueError("incompatible input dimensions {0}".format(coords.shape))
+        gram = np.empty((self.ndim, self.ndim))
+        flags = C.c_int()
+        self._check(lib().eb_walkers_gram(self._h, _as_dp(coords), coords.shape[0], _as_dp(gram), C.byref(flags)))
+        return gram, int(flags.value)
 
     def compute_log_prob(self, coords):
         coords = _f64(coords)

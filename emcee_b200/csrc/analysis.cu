@@ -1,0 +1,219 @@
+// Chain analysis on the device: running moments of the ensemble (mean / covariance of a
+// store=False run), the Gram matrix behind the initial-state independence check, and the
+// walker-averaged autocorrelation function of a stored chain.
+//
+// Reference semantics (file:line relative to the reference):
+//   chain mean / covariance of a run ........ what a caller computes from get_chain(flat=True)
+//                                              (backends/backend.py:42-58); here accumulated on the
+//                                              device so that store=False runs (ensemble.py:287-291)
+//                                              need no D2H of the state
+//   walkers_independent ...................... ensemble.py:653-663
+//   autocorr.function_1d / integrated_time ... autocorr.py:21-46, 49-123
+#include <math.h>
+
+#include "engine.cuh"
+
+namespace eb {
+
+namespace {
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ===========================================================================
+// column statistics: mean of each column (fixed summation order) + non-finite flags
+// ===========================================================================
+// grid = ceil(D / 32) blocks of (32, 8) threads; thread (x, y) sums rows y, y+8, ... of column 32 b + x
+__global__ void __launch_bounds__(256) colmean_kernel(const double* __restrict__ X, int64_t nrows, int D,
+                                                      double* __restrict__ mean, int* status) {
+  __shared__ double part[8][33];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int d = blockIdx.x * 32 + x;
+  double acc = 0.0;
+  bool any_inf = false, any_nan = false;
+  if (d < D)
+    for (int64_t r = y; r < nrows; r += 8) {
+      const double v = X[(size_t)r * D + d];
+      acc += v;
+      any_inf |= isinf(v);
+      any_nan |= isnan(v);
+    }
+  part[y][x] = acc;
+  if (status) {
+    if (any_inf) atomicOr(status, FLAG_INF_PARAM);
+    if (any_nan) atomicOr(status, FLAG_NAN_PARAM);
+  }
+  __syncthreads();
+  if (y == 0 && d < D) {
+    double s = 0.0;
+    for (int k = 0; k < 8; ++k) s += part[k][x];
+    mean[d] = s / (double)nrows;
+  }
+}
+
+// ===========================================================================
+// second moments on the FP64 tensor pipe: S2 += (X - shift)^T (X - shift), S1 += sum(X - shift)
+// ===========================================================================
+// The D x D result is tiled into 8 x 8 blocks; only blocks (i <= j) are computed.  A CTA stages
+// CH rows in shared memory; warp w owns block pairs base + w, base + w + 8, ... (MAXB of them,
+// accumulators in registers) and walks the staged rows 4 at a time: one DMMA m8n8k4 per block per
+// 4 rows with A[g][t] = x[row t][8 i + g], B[t][g] = x[row t][8 j + g].  blockIdx.y selects the
+// group of 8 * MAXB block pairs (large D needs several passes over the rows).
+constexpr int MOM_WARPS = 8;
+constexpr int MOM_MAXB = 18;  // 8 * 18 = 144 >= 136 pairs of D = 128: one pass
+
+__global__ void __launch_bounds__(32 * MOM_WARPS)
+    moments_partial_kernel(const double* __restrict__ X, int64_t nrows, int D, const double* __restrict__ shift,
+                           double* __restrict__ partial, int CH, int RS) {
+  extern __shared__ double xs[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int nblk = (D + 7) >> 3, Dp = 8 * nblk;
+  const int npairs = nblk * (nblk + 1) / 2;
+  const int base = blockIdx.y * MOM_WARPS * MOM_MAXB;
+  int bi[MOM_MAXB], bj[MOM_MAXB];
+  double c0[MOM_MAXB], c1[MOM_MAXB];
+#pragma unroll
+  for (int m = 0; m < MOM_MAXB; ++m) {
+    const int p = base + warp + MOM_WARPS * m;
+    c0[m] = c1[m] = 0.0;
+    bi[m] = -1;
+    bj[m] = 0;
+    if (p < npairs) {  // row-major walk of the upper triangle: row i holds nblk - i pairs
+      int i = 0, rem = p;
+      while (rem >= nblk - i) {
+        rem -= nblk - i;
+        ++i;
+      }
+      bi[m] = i;
+      bj[m] = i + rem;
+    }
+  }
+  double s1[4] = {0.0, 0.0, 0.0, 0.0};  // column sums of dims tid, tid + 256, ... (pass 0 only; Dp <= 1024)
+  const int64_t nchunks = (nrows + CH - 1) / CH;
+  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    for (int idx = tid; idx < CH * Dp; idx += 32 * MOM_WARPS) {
+      const int r = idx / Dp, d = idx - r * Dp;
+      const int64_t row = chunk * CH + r;
+      double v = 0.0;
+      if (row < nrows && d < D) v = X[(size_t)row * D + d] - shift[d];
+      xs[r * RS + d] = v;
+    }
+    __syncthreads();
+    if (blockIdx.y == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int d = tid + 32 * MOM_WARPS * q;
+        if (d < Dp)
+          for (int r = 0; r < CH; ++r) s1[q] += xs[r * RS + d];
+      }
+    }
+    for (int k4 = 0; k4 < CH / 4; ++k4) {
+      const double* rowp = xs + (4 * k4 + t) * RS + g;
+#pragma unroll
+      for (int m = 0; m < MOM_MAXB; ++m) {
+        if (bi[m] >= 0) {  // warp-uniform
+          const double av = rowp[8 * bi[m]];
+          const double bv = rowp[8 * bj[m]];
+          dmma884(c0[m], c1[m], av, bv);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  double* out = partial + (size_t)blockIdx.x * ((size_t)Dp + (size_t)Dp * Dp);
+  if (blockIdx.y == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int d = tid + 32 * MOM_WARPS * q;
+      if (d < Dp) out[d] = s1[q];
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MOM_MAXB; ++m) {
+    if (bi[m] >= 0) {
+      double* o = out + Dp + (size_t)(8 * bi[m] + g) * Dp + 8 * bj[m] + 2 * t;
+      o[0] = c0[m];
+      o[1] = c1[m];
+    }
+  }
+}
+
+// acc[D + D*D] += sum over the CTA partials, in CTA order (deterministic); mirrors the lower triangle
+__global__ void moments_reduce_kernel(const double* __restrict__ partial, int nparts, int D, double* __restrict__ acc) {
+  const int nblk = (D + 7) >> 3, Dp = 8 * nblk;
+  const size_t stride = (size_t)Dp + (size_t)Dp * Dp;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)D + (size_t)D * D) return;
+  size_t src;
+  if (e < (size_t)D) {
+    src = e;
+  } else {
+    const size_t f = e - D;
+    int r = (int)(f / D), c = (int)(f - (size_t)r * D);
+    if ((r >> 3) > (c >> 3)) {
+      const int tmp = r;
+      r = c;
+      c = tmp;
+    }
+    src = (size_t)Dp + (size_t)r * Dp + c;
+  }
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * stride + src];
+  acc[e] += s;
+}
+
+}  // namespace
+
+// ---- host-side launchers -----------------------------------------------------------------
+cudaError_t launch_colmean(const double* X, int64_t nrows, int D, double* mean, int* status, cudaStream_t st) {
+  if (nrows <= 0 || D <= 0) return cudaSuccess;
+  colmean_kernel<<<(D + 31) / 32, 256, 0, st>>>(X, nrows, D, mean, status);
+  return cudaGetLastError();
+}
+
+int moments_grid(int D, int sm_count) {
+  const int nblk = (D + 7) / 8, Dp = 8 * nblk;
+  const size_t per = ((size_t)Dp + (size_t)Dp * Dp) * sizeof(double);
+  size_t g = ((size_t)64 << 20) / per;  // <= 64 MiB of partials
+  if (g < 1) g = 1;
+  if (g > (size_t)sm_count) g = (size_t)sm_count;
+  return (int)g;
+}
+
+size_t moments_partial_bytes(int D, int sm_count) {
+  const int nblk = (D + 7) / 8, Dp = 8 * nblk;
+  return (size_t)moments_grid(D, sm_count) * ((size_t)Dp + (size_t)Dp * Dp) * sizeof(double);
+}
+
+// acc[D + D*D] += [sum(x - shift), (x - shift)^T (x - shift)] over the rows of X
+cudaError_t launch_moments(const double* X, int64_t nrows, int D, const double* shift, double* partial, double* acc,
+                           int sm_count, cudaStream_t st) {
+  if (D > 1024) return cudaErrorNotSupported;
+  if (nrows <= 0) return cudaSuccess;
+  const int nblk = (D + 7) / 8, Dp = 8 * nblk;
+  int RS = Dp;
+  while (RS % 32 != 8) RS += 8;  // 4 staged rows x 8 dims of one fragment hit 32 distinct 8-byte banks
+  int CH = (int)((96 * 1024) / ((size_t)RS * sizeof(double))) & ~3;
+  if (CH > 64) CH = 64;
+  if (CH < 4) CH = 4;
+  const size_t smem = (size_t)CH * RS * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(moments_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int grid = moments_grid(D, sm_count);
+  const int64_t nchunks = (nrows + CH - 1) / CH;
+  if (grid > nchunks) grid = (int)nchunks;
+  const int npairs = nblk * (nblk + 1) / 2;
+  const int passes = (npairs + MOM_WARPS * MOM_MAXB - 1) / (MOM_WARPS * MOM_MAXB);
+  moments_partial_kernel<<<dim3(grid, passes), 32 * MOM_WARPS, smem, st>>>(X, nrows, D, shift, partial, CH, RS);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const size_t n = (size_t)D + (size_t)D * D;
+  moments_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, grid, D, acc);
+  return cudaGetLastError();
+}
+
+}  // namespace eb

@@ -79,6 +79,20 @@ struct eb_ctx {
   bool fused_last = false;  // the last dense_dmma launch carried the P2P barrier itself
   int dmma_stagger = 1;
   int dmma_group = 1;  // half-steps per persistent dense_dmma launch (1: a launch per half-step)
+  bool pdl = true;       // dense_dmma launches chain as programmatic dependents (prologue overlaps the previous tail)
+  bool chain_ok = false; // the last operation enqueued on the stream is a dense_dmma kernel of this run
+  // multi-GPU: log_prob / accept mask / counters (and, P2P, coords) of rows owned by OTHER ranks are stale
+  // on this rank until the next collective read (eb_get_state, eb_get_naccepted, ...) replicates them
+  bool replicas_dirty = false;
+
+  // running chain moments (eb_moments): sum of (x - shift) and of its outer product over the owned
+  // rows of every `moments_every`-th step
+  uint64_t moments_every = 0;
+  double* mom_acc = nullptr;      // [D + D*D] accumulators
+  double* mom_shift = nullptr;    // [D]
+  double* mom_partial = nullptr;  // per-CTA partials of one accumulation
+  unsigned long long mom_count = 0;
+  bool mom_have_shift = false;
 
   Comm comm;  // multi-GPU (comm.h)
 
@@ -238,6 +252,9 @@ int eb_destroy(eb_ctx* c) {
     if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
   }
   cudaFree(c->flush_buf);
+  cudaFree(c->mom_acc);
+  cudaFree(c->mom_shift);
+  cudaFree(c->mom_partial);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   cudaFree(c->timeline);
   cudaFree(c->tap_partners);
@@ -367,26 +384,71 @@ int eb_compute_log_prob(eb_ctx* c, const double* coords, size_t m, double* out) 
 }
 
 // ---- state -------------------------------------------------------------------
+// rows [r0, r1) this context owns (the whole ensemble on one GPU)
+static void owned_rows(const eb_ctx* c, int64_t& r0, int64_t& r1) {
+  r0 = 0;
+  r1 = c->N;
+  if (c->comm.nranks > 1) {
+    r0 = c->comm.rows_per_rank * c->comm.rank;
+    r1 = r0 + c->comm.rows_per_rank;
+  }
+}
+
+// multi-GPU: make log_prob / accept mask / counters (and coords in P2P mode) of every rank's rows
+// valid on this rank.  COLLECTIVE: every rank calls it at the same point (the Python layer does).
+static int sync_replicas(eb_ctx* c) {
+  if (c->comm.nranks == 1 || !c->replicas_dirty) return EB_OK;
+  uint64_t launches = 0;
+  c->chain_ok = false;
+  if (comm_sync_state(c->comm, c->st, c->status_dev, c->logp, c->accepted, c->nacc, launches))
+    FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+  c->fused_last = false;
+  CK(c, cudaStreamSynchronize(c->st));
+  c->replicas_dirty = false;
+  return EB_OK;
+}
+
 int eb_set_state(eb_ctx* c, const double* coords, const double* log_prob) {
   if (!c) return EB_ERR_INVALID;
   if (!coords) FAIL(c, EB_ERR_INVALID, "eb_set_state: coords is null");
   if (!c->have_model) FAIL(c, EB_ERR_STATE, "eb_set_state: no model set");
   CK(c, cudaSetDevice(c->device));
-  const size_t nd = (size_t)c->N * (size_t)c->D;
+  const size_t D = (size_t)c->D;
   c->have_state = false;
+  c->chain_ok = false;
   if (log_prob) {
     for (int64_t w = 0; w < c->N; ++w)
       if (isnan(log_prob[w])) FAIL(c, EB_ERR_NAN_INITIAL, "The initial log_prob was NaN");  // ensemble.py:357-358
   }
-  CK(c, cudaMemcpyAsync(c->coords, coords, nd * sizeof(double), cudaMemcpyHostToDevice, c->st));
-  if (log_prob) {
-    CK(c, cudaMemcpyAsync(c->logp, log_prob, (size_t)c->N * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    CK(c, cudaStreamSynchronize(c->st));
-  } else {
-    CK(c, launch_logprob(c, c->coords, c->N, c->logp));
-    int rc = fetch_status(c);
-    if (rc) return rc;
+  // Sharded ensembles: only the rows this rank owns cross PCIe (the host arrays are still indexed by
+  // global walker id); non-owned rows are never read by the kernels in P2P mode and are filled by one
+  // all-gather in EB_COMM_ALLGATHER mode.
+  int64_t r0, r1;
+  owned_rows(c, r0, r1);
+  const size_t rows = (size_t)(r1 - r0);
+  uint64_t launches = 0;
+  if (c->comm.nranks > 1 && c->comm.mode == EB_COMM_P2P && c->comm.imported) {
+    // no peer may still be pulling the rows that are about to be overwritten
+    if (comm_barrier(c->comm, c->st, c->status_dev, launches)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+    c->fused_last = false;
   }
+  CK(c, cudaMemcpyAsync(c->coords + (size_t)r0 * D, coords + (size_t)r0 * D, rows * D * sizeof(double),
+                        cudaMemcpyHostToDevice, c->st));
+  if (log_prob) {
+    CK(c, cudaMemcpyAsync(c->logp + r0, log_prob + r0, rows * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  } else {
+    CK(c, launch_logprob(c, c->coords + (size_t)r0 * D, (int64_t)rows, c->logp + r0));
+  }
+  if (c->comm.nranks > 1) {
+    if (c->comm.mode == EB_COMM_ALLGATHER && comm_gather_coords(c->comm, c->st, launches))
+      FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+    if (c->comm.mode == EB_COMM_P2P && c->comm.imported &&
+        comm_barrier(c->comm, c->st, c->status_dev, launches))  // every rank's block is in place
+      FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+    c->replicas_dirty = true;
+  }
+  int rc = fetch_status(c);
+  if (rc) return rc;
   c->have_state = true;
   return EB_OK;
 }
@@ -395,11 +457,44 @@ int eb_get_state(eb_ctx* c, double* coords, double* log_prob) {
   if (!c) return EB_ERR_INVALID;
   if (!c->have_state) FAIL(c, EB_ERR_STATE, "eb_get_state: no state set");
   CK(c, cudaSetDevice(c->device));
+  int rc = sync_replicas(c);  // multi-GPU: the GLOBAL state (collective)
+  if (rc) return rc;
+  c->chain_ok = false;
   if (coords)
     CK(c, cudaMemcpyAsync(coords, c->coords, (size_t)c->N * c->D * sizeof(double), cudaMemcpyDeviceToHost,
                           c->st));
   if (log_prob)
     CK(c, cudaMemcpyAsync(log_prob, c->logp, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CK(c, cudaStreamSynchronize(c->st));
+  return EB_OK;
+}
+
+int eb_owned_rows(const eb_ctx* c, int64_t* row0, int64_t* nrows) {
+  if (!c) return EB_ERR_INVALID;
+  int64_t r0, r1;
+  owned_rows(c, r0, r1);
+  if (row0) *row0 = r0;
+  if (nrows) *nrows = r1 - r0;
+  return EB_OK;
+}
+
+int eb_get_state_rows(eb_ctx* c, int64_t row0, int64_t nrows, double* coords, double* log_prob) {
+  if (!c) return EB_ERR_INVALID;
+  if (!c->have_state) FAIL(c, EB_ERR_STATE, "eb_get_state_rows: no state set");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > c->N) FAIL(c, EB_ERR_INVALID, "eb_get_state_rows: rows out of range");
+  int64_t r0, r1;
+  owned_rows(c, r0, r1);
+  if (c->replicas_dirty && (row0 < r0 || row0 + nrows > r1))
+    FAIL(c, EB_ERR_STATE, "eb_get_state_rows: rows [%lld, %lld) are owned by another rank and not replicated here; "
+         "read the owned block [%lld, %lld) or call eb_get_state (collective) first",
+         (long long)row0, (long long)(row0 + nrows), (long long)r0, (long long)r1);
+  CK(c, cudaSetDevice(c->device));
+  c->chain_ok = false;
+  if (coords && nrows)
+    CK(c, cudaMemcpyAsync(coords, c->coords + (size_t)row0 * c->D, (size_t)nrows * c->D * sizeof(double),
+                          cudaMemcpyDeviceToHost, c->st));
+  if (log_prob && nrows)
+    CK(c, cudaMemcpyAsync(log_prob, c->logp + row0, (size_t)nrows * sizeof(double), cudaMemcpyDeviceToHost, c->st));
   CK(c, cudaStreamSynchronize(c->st));
   return EB_OK;
 }
@@ -542,6 +637,13 @@ int launch_step_generic(eb_ctx* c, const eb_move& mv, uint64_t step, const int32
       ++k;
     }
     comm_active_range(c->comm, a, step_in_chunk);  // i_lo / i_hi for this rank
+    if (c->fused_last) {
+      // the previous launch was a dense_dmma kernel that carried the peer barrier itself (signal at its end);
+      // this kernel does not wait on its own, so the ranks meet explicitly before it reads peer rows
+      if (comm_barrier(c->comm, c->st, c->status_dev, launches)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+      c->fused_last = false;
+    }
+    c->chain_ok = false;
     bool used_tma = false;
     if (c->allow_tma && !c->debug) CK(c, launch_half_step_tma(mv.kind, a, c->sm_count, c->st, &used_tma));
     if (used_tma) {
@@ -572,13 +674,16 @@ int flush_dmma(eb_ctx* c, const eb_move& mv, DmmaGroup& grp, uint64_t& launches)
   a.range = c->comm.nranks > 1 ? c->comm.ranges : nullptr;
   int bound = grp.max_count;
   if (c->comm.nranks > 1 && c->comm.rows_per_rank < bound) bound = (int)c->comm.rows_per_rank;
-  const bool fused = grp.nhalf == 1 && comm_fuse_barrier(c->comm, a);  // P2P: barrier inside the kernel
+  // P2P: the peer barrier rides inside the kernel (wait at its start, between its half-steps, signal at its end)
+  const bool fused = comm_fuse_barrier(c->comm, a, grp.nhalf);
   c->fused_last = fused;
+  const bool pdl = c->pdl && c->chain_ok && grp.nhalf == 1;
   int grid = 0;
-  CK(c, launch_dense_dmma(a, c->descs_host[grp.first], c->descs_dev + grp.first, grp.nhalf, bound, c->gbar, c->gbar_count, c->sm_count, &grid,
-                          c->st));
+  CK(c, launch_dense_dmma(a, c->descs_host[grp.first], c->descs_dev + grp.first, grp.nhalf, bound, c->gbar, c->gbar_count, c->sm_count, pdl,
+                          &grid, c->st));
   c->gbar_count += (unsigned long long)(grp.nhalf - 1) * (unsigned long long)grid;
   c->last_kernel = "dense_dmma";
+  c->chain_ok = grid > 0;
   ++launches;
   grp = DmmaGroup{};
   return EB_OK;
@@ -587,6 +692,8 @@ int flush_dmma(eb_ctx* c, const eb_move& mv, DmmaGroup& grp, uint64_t& launches)
 // run nsteps steps.  `after_step(k)` is called with the work of step k enqueued and may
 // enqueue copies on the stream; `sync_every` > 0 tells how often it actually does (every
 // sync_every-th step), so that steps in between can share one persistent launch.
+int accumulate_moments(eb_ctx* c, uint64_t& launches);  // below
+
 template <class F>
 int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every, F&& after_step) {
   uint64_t launches = 0;
@@ -600,9 +707,13 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
       c->ev_pool.push_back(e);
     }
   }
+  c->chain_ok = false;
   CK(c, cudaEventRecord(c->ev0, c->st));
   if (comm_begin(c->comm, c->st, c->status_dev, launches)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+  c->fused_last = false;
   const bool multi = c->comm.nranks > 1;
+  // ranks that exchange whole row blocks through NCCL do so after every split: one half-step per launch
+  const bool exchange_each = multi && c->comm.mode == EB_COMM_ALLGATHER;
   std::vector<size_t> pick;
   uint64_t done = 0;
   while (done < nsteps) {
@@ -664,11 +775,14 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
       if (perstep) {
         CK(c, cudaMemsetAsync(c->flush_buf, (int)(k & 0xff), c->flush_bytes, c->st));
         CK(c, cudaEventRecord(c->ev_pool[2 * (done + k)], c->st));
+        c->chain_ok = false;
       }
       if (k == 0) {
         // dense_dmma descriptors of the chunk and, when needed, the split tables (charged to this step)
-        if (ndesc)
+        if (ndesc) {
           CK(c, cudaMemcpyAsync(c->descs_dev, c->descs_host, ndesc * sizeof(HalfDesc), cudaMemcpyHostToDevice, c->st));
+          c->chain_ok = false;
+        }
         if (build) {
           CK(c, cudaMemcpyAsync(c->info_dev, c->info_host, build * sizeof(StepInfo), cudaMemcpyHostToDevice, c->st));
           const Comm& cm = c->comm;
@@ -676,6 +790,7 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
                                     cm.rows_per_rank * cm.rank, cm.rows_per_rank * (cm.rank + 1),
                                     cm.nranks > 1 ? cm.ranges : nullptr, c->st));
           ++launches;
+          c->chain_ok = false;
         }
       }
       int rc;
@@ -693,18 +808,18 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
           grp.nhalf += 1;
           grp.max_count = std::max(grp.max_count, (int)d.a_count);
           ++desc_cursor;
-          if (!multi && grp.nhalf >= c->dmma_group && split + 1 < mv.nsplits) {
+          if (exchange_each || (grp.nhalf >= c->dmma_group && split + 1 < mv.nsplits)) {
             rc = flush_dmma(c, mv, grp, launches);
             if (rc) return rc;
-          }
-          if (multi) {  // ranks exchange rows after every split: one half-step per launch
-            rc = flush_dmma(c, mv, grp, launches);
-            if (rc) return rc;
-            if (!c->fused_last && comm_after_split(c->comm, c->st, c->status_dev, launches))
-              FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+            if (exchange_each) {
+              c->chain_ok = false;
+              if (comm_after_split(c->comm, c->st, c->status_dev, launches))
+                FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+            }
           }
         }
-        const bool host_event = perstep || (sync_every > 0 && (done + k + 1) % sync_every == 0);
+        const bool moments_now = c->moments_every > 0 && (c->step + 1) % c->moments_every == 0;
+        const bool host_event = perstep || moments_now || (sync_every > 0 && (done + k + 1) % sync_every == 0);
         if (host_event || k + 1 == chunk || grp.nhalf >= c->dmma_group) {
           rc = flush_dmma(c, mv, grp, launches);
           if (rc) return rc;
@@ -718,17 +833,24 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
         if (rc) return rc;
       }
       c->step += 1;
-      if (perstep) CK(c, cudaEventRecord(c->ev_pool[2 * (done + k) + 1], c->st));
+      if (c->moments_every > 0 && c->step % c->moments_every == 0) {
+        rc = accumulate_moments(c, launches);
+        if (rc) return rc;
+      }
+      if (perstep) {
+        CK(c, cudaEventRecord(c->ev_pool[2 * (done + k) + 1], c->st));
+        c->chain_ok = false;
+      }
       rc = after_step(done + k);
       if (rc) return rc;
     }
     done += chunk;
   }
   CK(c, cudaEventRecord(c->ev1, c->st));
-  // replicate log_prob / accept mask / counters across ranks (outside the timed bracket: it is
-  // bookkeeping for eb_get_state, not part of a step)
-  if (comm_sync_state(c->comm, c->st, c->status_dev, c->logp, c->accepted, c->nacc, launches))
-    FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+  c->chain_ok = false;
+  // multi-GPU: the rows of other ranks are NOT replicated here; collective readers (eb_get_state,
+  // eb_get_naccepted, the accept mask of eb_step) do that on demand, sharded readers never need it
+  if (multi) c->replicas_dirty = true;
   CK(c, cudaMemcpyAsync(c->status_host, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   CK(c, cudaStreamSynchronize(c->st));
   float ms = 0.f;
@@ -745,6 +867,42 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
   }
   c->last_launches = launches;
   return check_status(c);
+}
+
+// ---- running chain moments ---------------------------------------------------------------------
+int moments_config(eb_ctx* c, uint64_t every) {
+  CK(c, cudaSetDevice(c->device));
+  if (every > 0 && c->D > 1024) FAIL(c, EB_ERR_UNSUPPORTED, "chain moments are limited to ndim <= 1024");
+  const size_t n = (size_t)c->D + (size_t)c->D * c->D;
+  if (every > 0 && !c->mom_acc) {
+    CK(c, cudaMalloc(&c->mom_acc, n * sizeof(double)));
+    CK(c, cudaMalloc(&c->mom_shift, (size_t)c->D * sizeof(double)));
+    if (!c->mom_partial) CK(c, cudaMalloc(&c->mom_partial, moments_partial_bytes(c->D, c->sm_count)));
+  }
+  if (c->mom_acc) CK(c, cudaMemsetAsync(c->mom_acc, 0, n * sizeof(double), c->st));
+  c->mom_count = 0;
+  c->mom_have_shift = false;
+  c->moments_every = every;
+  CK(c, cudaStreamSynchronize(c->st));
+  return EB_OK;
+}
+
+// fold the rows this rank owns of the CURRENT state into the accumulators (enqueued on the stream)
+int accumulate_moments(eb_ctx* c, uint64_t& launches) {
+  int64_t r0, r1;
+  owned_rows(c, r0, r1);
+  const double* X = c->coords + (size_t)r0 * c->D;
+  c->chain_ok = false;
+  if (!c->mom_have_shift) {
+    // shift = the ensemble mean at the first accumulation: keeps the raw second moments well conditioned
+    CK(c, launch_colmean(X, r1 - r0, c->D, c->mom_shift, nullptr, c->st));
+    c->mom_have_shift = true;
+    ++launches;
+  }
+  CK(c, launch_moments(X, r1 - r0, c->D, c->mom_shift, c->mom_partial, c->mom_acc, c->sm_count, c->st));
+  launches += 2;
+  c->mom_count += (unsigned long long)(r1 - r0);
+  return EB_OK;
 }
 
 int step_preflight(eb_ctx* c) {
@@ -770,6 +928,8 @@ int eb_step(eb_ctx* c, const eb_move* moves, size_t nmoves, uint64_t nsteps, uin
     if (rc) return rc;
   }
   if (accepted_last) {
+    rc = sync_replicas(c);  // multi-GPU: the mask of every rank's rows (collective)
+    if (rc) return rc;
     CK(c, cudaMemcpyAsync(accepted_last, c->accepted, (size_t)c->N, cudaMemcpyDeviceToHost, c->st));
     CK(c, cudaStreamSynchronize(c->st));
   }
@@ -815,6 +975,15 @@ int eb_step_store(eb_ctx* c, const eb_move* moves, size_t nmoves, uint64_t nstep
     const int slot = (int)(stored & 1);
     int r = drain(slot);
     if (r) return r;
+    c->chain_ok = false;
+    if (c->comm.nranks > 1) {
+      // a stored step holds EVERY walker: replicate the other ranks' rows (log_prob, accept mask and, in
+      // P2P mode, coords) before the copy -- the in-run exchange only moves what the kernels need
+      uint64_t l = 0;
+      if (comm_sync_state(c->comm, c->st, c->status_dev, c->logp, c->accepted, nullptr, l))
+        FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
+      c->fused_last = false;
+    }
     CK(c, cudaMemcpyAsync(c->stage[slot], c->coords, N * D * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     CK(c, cudaMemcpyAsync(c->stage[slot] + N * D, c->logp, N * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     CK(c, cudaMemcpyAsync(c->stage_acc[slot], c->accepted, N, cudaMemcpyDeviceToHost, c->st));
@@ -833,6 +1002,8 @@ int eb_step_store(eb_ctx* c, const eb_move* moves, size_t nmoves, uint64_t nstep
 int eb_get_naccepted(eb_ctx* c, uint64_t* naccepted) {
   if (!c || !naccepted) return EB_ERR_INVALID;
   CK(c, cudaSetDevice(c->device));
+  int rc = sync_replicas(c);  // multi-GPU: every rank's counters (collective)
+  if (rc) return rc;
   CK(c, cudaMemcpyAsync(naccepted, c->nacc, (size_t)c->N * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->st));
   CK(c, cudaStreamSynchronize(c->st));
   return EB_OK;
@@ -843,6 +1014,95 @@ int eb_reset_counters(eb_ctx* c) {
   CK(c, cudaSetDevice(c->device));
   CK(c, cudaMemsetAsync(c->nacc, 0, (size_t)c->N * sizeof(unsigned long long), c->st));
   CK(c, cudaStreamSynchronize(c->st));
+  return EB_OK;
+}
+
+int eb_moments(eb_ctx* c, double* mean, double* cov, uint64_t* count, uint64_t* naccepted_total) {
+  if (!c) return EB_ERR_INVALID;
+  if (!c->mom_acc) FAIL(c, EB_ERR_STATE, "eb_moments: enable with eb_set_option(\"moments_every\", n) before stepping");
+  CK(c, cudaSetDevice(c->device));
+  const size_t D = (size_t)c->D, n = D + D * D;
+  std::vector<double> acc(n), shift(D);
+  CK(c, cudaMemcpyAsync(acc.data(), c->mom_acc, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CK(c, cudaMemcpyAsync(shift.data(), c->mom_shift, D * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  std::vector<unsigned long long> nacc;
+  int64_t r0, r1;
+  owned_rows(c, r0, r1);
+  if (naccepted_total) {
+    nacc.resize((size_t)(r1 - r0));
+    CK(c, cudaMemcpyAsync(nacc.data(), c->nacc + r0, nacc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                          c->st));
+  }
+  CK(c, cudaStreamSynchronize(c->st));
+  c->chain_ok = false;
+  const double m = (double)c->mom_count;
+  if (count) *count = c->mom_count;
+  if (naccepted_total) {
+    unsigned long long tot = 0;
+    for (unsigned long long v : nacc) tot += v;
+    *naccepted_total = tot;
+  }
+  if (c->mom_count == 0) {
+    if (mean) std::fill(mean, mean + D, NAN);
+    if (cov) std::fill(cov, cov + D * D, NAN);
+    return EB_OK;
+  }
+  // mean = shift + S1 / m ; cov = (S2 - S1 S1^T / m) / (m - 1)   (np.cov(flatchain, rowvar=False))
+  if (mean)
+    for (size_t d = 0; d < D; ++d) mean[d] = shift[d] + acc[d] / m;
+  if (cov)
+    for (size_t r = 0; r < D; ++r)
+      for (size_t k = 0; k < D; ++k)
+        cov[r * D + k] = (acc[D + r * D + k] - acc[r] * acc[k] / m) / (m - 1.0);
+  return EB_OK;
+}
+
+int eb_walkers_gram(eb_ctx* c, const double* coords, size_t rows, double* gram, int* flags) {
+  if (!c) return EB_ERR_INVALID;
+  if (!coords || !gram || rows == 0) FAIL(c, EB_ERR_INVALID, "eb_walkers_gram: null buffer");
+  if (c->D > 1024) FAIL(c, EB_ERR_UNSUPPORTED, "eb_walkers_gram is limited to ndim <= 1024");
+  CK(c, cudaSetDevice(c->device));
+  int rc = ensure_scratch(c, rows);
+  if (rc) return rc;
+  const size_t D = (size_t)c->D, n = D + D * D;
+  double* work = nullptr;  // [D mean | D + D*D accumulators]
+  CK(c, cudaMalloc(&work, (D + n) * sizeof(double)));
+  if (!c->mom_partial) {
+    cudaError_t e = cudaMalloc(&c->mom_partial, moments_partial_bytes(c->D, c->sm_count));
+    if (e != cudaSuccess) {
+      cudaFree(work);
+      CK(c, e);
+    }
+  }
+  c->chain_ok = false;
+  std::vector<double> acc(n);
+  int f = 0;
+  cudaError_t e = cudaMemcpyAsync(c->scratch_x, coords, rows * D * sizeof(double), cudaMemcpyHostToDevice, c->st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(work, 0, (D + n) * sizeof(double), c->st);
+  if (e == cudaSuccess) e = launch_colmean(c->scratch_x, (int64_t)rows, c->D, work, c->status_dev, c->st);
+  if (e == cudaSuccess)
+    e = launch_moments(c->scratch_x, (int64_t)rows, c->D, work, c->mom_partial, work + D, c->sm_count, c->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(acc.data(), work + D, n * sizeof(double), cudaMemcpyDeviceToHost, c->st);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(c->status_host, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, c->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+  cudaFree(work);
+  CK(c, e);
+  // the non-finite flags are an ANSWER here (walkers_independent returns False), not an error
+  if (*c->status_host & (FLAG_INF_PARAM | FLAG_NAN_PARAM)) f |= 1;
+  *c->status_host = 0;
+  CK(c, cudaMemsetAsync(c->status_dev, 0, sizeof(int), c->st));
+  CK(c, cudaStreamSynchronize(c->st));
+  // centred, column-normalised walkers C (ensemble.py:656-661): C^T C = M_jk / sqrt(M_jj M_kk); the
+  // max-abs scaling of :658-659 cancels, it only matters as the zero-span test
+  for (size_t j = 0; j < D; ++j)
+    if (!(acc[D + j * D + j] > 0.0)) f |= 2;
+  for (size_t j = 0; j < D; ++j)
+    for (size_t k = 0; k < D; ++k) {
+      const double den = sqrt(acc[D + j * D + j] * acc[D + k * D + k]);
+      gram[j * D + k] = den > 0.0 ? acc[D + j * D + k] / den : 0.0;
+    }
+  if (flags) *flags = f;
   return EB_OK;
 }
 
@@ -893,6 +1153,14 @@ int eb_set_option(eb_ctx* c, const char* name, int64_t value) {
     if (value < 1) FAIL(c, EB_ERR_INVALID, "dmma_group must be >= 1");
     c->dmma_group = (int)std::min<int64_t>(value, 1 << 20);
     return EB_OK;
+  }
+  if (!strcmp(name, "pdl")) {
+    c->pdl = value != 0;
+    return EB_OK;
+  }
+  if (!strcmp(name, "moments_every")) {
+    if (value < 0) FAIL(c, EB_ERR_INVALID, "moments_every must be >= 0");
+    return moments_config(c, (uint64_t)value);
   }
   if (!strcmp(name, "tma_rows")) {
     c->allow_tma = value != 0;
@@ -955,6 +1223,7 @@ int eb_comm_init(eb_ctx* c, const char id[EB_COMM_ID_BYTES], int rank, int nrank
   if (!c) return EB_ERR_INVALID;
   CK(c, cudaSetDevice(c->device));
   c->tbl_n = 0;  // the cached split tables carry the old ownership ranges
+  c->have_state = false;  // ownership changes: the state must be set again through the sharded path
   unsigned* flags = reinterpret_cast<unsigned*>(c->coords + (size_t)c->N * c->D);
   if (comm_init(c->comm, id, rank, nranks, mode, c->N, c->D, c->coords, flags, c->table_cap, c->st))
     FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());

@@ -331,7 +331,7 @@ static int p2p_barrier(Comm& c, cudaStream_t st, int* status, uint64_t& launches
   return 0;
 }
 
-bool comm_fuse_barrier(Comm& c, HalfStepArgs& a) {
+bool comm_fuse_barrier(Comm& c, HalfStepArgs& a, int nhalf) {
   if (c.nranks == 1 || c.mode != EB_COMM_P2P || !c.imported) return false;
   a.p2p_peer_flags = c.peer_flags_dev;
   a.p2p_my_flags = c.flags;
@@ -339,9 +339,14 @@ bool comm_fuse_barrier(Comm& c, HalfStepArgs& a) {
   a.p2p_rank = c.rank;
   a.p2p_nranks = c.nranks;
   a.p2p_wait = c.epoch;        // everybody has finished the previous barrier event
-  a.p2p_signal = c.epoch + 1;  // ... and this kernel's completion is the next one
-  c.epoch += 1;
+  a.p2p_signal = c.epoch + 1;  // ... the completion of this launch's half-step h is event epoch + 1 + h
+  c.epoch += (unsigned)nhalf;
   return true;
+}
+
+int comm_barrier(Comm& c, cudaStream_t st, int* status, uint64_t& launches) {
+  if (c.nranks == 1 || c.mode != EB_COMM_P2P) return 0;
+  return p2p_barrier(c, st, status, launches);
 }
 
 int comm_begin(Comm& c, cudaStream_t st, int* status, uint64_t& launches) {
@@ -368,14 +373,28 @@ int comm_sync_state(Comm& c, cudaStream_t st, int* status, double* logp, uint8_t
   ncclComm_t comm = static_cast<ncclComm_t>(c.nccl);
   const size_t R = (size_t)c.rows_per_rank;
   if (c.mode == EB_COMM_P2P) {  // replicas were not maintained during the run
+    // nobody may still be pulling rows of the last half-step when the gathers start rewriting replicas
+    if (p2p_barrier(c, st, status, launches)) return 1;
     NCK(c, api.AllGather(c.coords + (size_t)c.rank * R * c.D, c.coords, R * c.D, ncclDouble, comm, st));
     ++launches;
   }
   NCK(c, api.AllGather(logp + c.rank * R, logp, R, ncclDouble, comm, st));
   NCK(c, api.AllGather(accepted + c.rank * R, accepted, R, ncclUint8, comm, st));
-  NCK(c, api.AllGather(nacc + c.rank * R, nacc, R, ncclUint64, comm, st));
-  launches += 3;
+  launches += 2;
+  if (nacc) {
+    NCK(c, api.AllGather(nacc + c.rank * R, nacc, R, ncclUint64, comm, st));
+    ++launches;
+  }
   if (c.mode == EB_COMM_P2P) return p2p_barrier(c, st, status, launches);  // gathers landed everywhere
+  return 0;
+}
+
+int comm_gather_coords(Comm& c, cudaStream_t st, uint64_t& launches) {
+  if (c.nranks == 1) return 0;
+  const size_t cnt = (size_t)c.rows_per_rank * c.D;
+  NCK(c, nccl_api().AllGather(c.coords + (size_t)c.rank * cnt, c.coords, cnt, ncclDouble,
+                              static_cast<ncclComm_t>(c.nccl), st));
+  ++launches;
   return 0;
 }
 

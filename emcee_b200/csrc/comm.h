@@ -51,12 +51,19 @@ void comm_active_range(const Comm& c, HalfStepArgs& a, size_t step_in_chunk);
 // P2P: all ranks rendezvous before the first split of a call
 int comm_begin(Comm& c, cudaStream_t st, int* status, uint64_t& launches);
 // P2P + dense_dmma: the barrier rides inside the half-step kernel (wait at its start, signal from
-// its last CTA); fills the p2p_* fields and advances the epoch.  Returns false if not applicable.
-bool comm_fuse_barrier(Comm& c, HalfStepArgs& a);
+// its last CTA, and between the `nhalf` half-steps of a persistent launch); fills the p2p_* fields and
+// advances the epoch by nhalf.  Returns false if not applicable.
+bool comm_fuse_barrier(Comm& c, HalfStepArgs& a, int nhalf);
+// P2P: an explicit rendezvous on the stream (publish the next epoch, wait for every peer's); needed
+// between a kernel that carried the barrier itself and a consumer that does not wait on its own
+int comm_barrier(Comm& c, cudaStream_t st, int* status, uint64_t& launches);
 // make the rows updated in this split visible to every rank
 int comm_after_split(Comm& c, cudaStream_t st, int* status, uint64_t& launches);
-// end of a stepping call: replicate log_prob / accept mask / counters (and coords in P2P mode)
+// replicate log_prob / accept mask / counters (nacc may be null) -- and coords in P2P mode -- on every rank
 int comm_sync_state(Comm& c, cudaStream_t st, int* status, double* logp, uint8_t* accepted,
                     unsigned long long* nacc, uint64_t& launches);
+// one in-place all-gather of the owned row blocks of coords (used after a sharded eb_set_state in
+// EB_COMM_ALLGATHER mode, where kernels read partner rows from the local replica)
+int comm_gather_coords(Comm& c, cudaStream_t st, uint64_t& launches);
 
 }  // namespace eb

@@ -102,10 +102,21 @@ struct HalfDesc {
 // runs `nhalf` consecutive half-steps in ONE cooperative launch (grid barrier between them);
 // a.order / a.range point at the chunk's table bases; d0 == descs[0] travels by value.  max_count bounds the active ranks per
 // half-step (grid sizing).  gbar is a monotonic global counter, gbar_base its value at launch.
+// `pdl`: launch as a programmatic dependent of the previous kernel in the stream (nhalf == 1 only; the caller
+// guarantees that kernel is a dense_dmma launch of the same run).
 cudaError_t launch_dense_dmma(const HalfStepArgs& a, const HalfDesc& d0, const HalfDesc* descs_dev, int nhalf,
                               int max_count,
-                              unsigned long long* gbar, unsigned long long gbar_base, int sm_count, int* grid_out,
-                              cudaStream_t st);
+                              unsigned long long* gbar, unsigned long long gbar_base, int sm_count, bool pdl,
+                              int* grid_out, cudaStream_t st);
+
+// ---- chain analysis (analysis.cu) ------------------------------------------------------------
+// column means of X[nrows, D] (fixed summation order); status (nullable) gets the non-finite flags
+cudaError_t launch_colmean(const double* X, int64_t nrows, int D, double* mean, int* status, cudaStream_t st);
+// acc[D + D*D] += [sum(x - shift), (x - shift)^T (x - shift)] over the rows of X (DMMA; D <= 1024);
+// partial: scratch of moments_partial_bytes(D, sm_count)
+size_t moments_partial_bytes(int D, int sm_count);
+cudaError_t launch_moments(const double* X, int64_t nrows, int D, const double* shift, double* partial, double* acc,
+                           int sm_count, cudaStream_t st);
 
 inline int lanes_per_walker(int D) {
   int g = 4;

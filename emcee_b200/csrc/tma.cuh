@@ -38,6 +38,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     if (clock64() - t0 > 240000000000ll) __trap();
   }
 }
+// Abortable wait for kernels whose producers may give up on a lost peer GPU: `abort` is a CTA-wide
+// shared-memory flag the producers set on a barrier timeout; every warp of the CTA then leaves
+// instead of spinning into the trap, and the host reports FLAG_COMM_TIMEOUT as EB_ERR_COMM.
+__device__ __forceinline__ bool mbar_wait_abortable(uint64_t* bar, unsigned parity, const volatile int* abort) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*abort) return false;
+    if (clock64() - t0 > 240000000000ll) __trap();
+  }
+  return true;
+}
 // best-effort wait of at most `cycles`: for orderings that are optimisations, not dependencies
 __device__ __forceinline__ void mbar_wait_for(uint64_t* bar, unsigned parity, long long cycles) {
   const long long t0 = clock64();
@@ -63,5 +75,14 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA store source)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+
+// programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute starts while its predecessor in the stream is still draining; everything that reads or
+// writes what the predecessor touches sits behind pdl_wait().  Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// pull one 128-byte line into L2 (no register, no L1 allocation)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 }  // namespace eb

@@ -97,6 +97,15 @@ class EnsembleSampler(object):
             self._moves, weights = [moves], [1.0]
         self._raw_weights = np.atleast_1d(weights).astype(float)
         self._weights = self._raw_weights / np.sum(self._raw_weights)
+        for m in self._moves:
+            # the step loop runs inside the CUDA library: a move must be one of the device moves
+            # (it only *describes* itself); a host ``Move`` with its own ``propose`` cannot be called
+            # back from a kernel -- say so here, not with an AttributeError in the middle of sample()
+            if not callable(getattr(m, "descriptor", None)):
+                raise TypeError(
+                    "moves must be emcee_b200.moves.* device moves; got {0!r}, which has no device "
+                    "descriptor (host-side Move subclasses cannot run inside the fused step kernels)".format(m)
+                )
 
         self.pool = None
         self.vectorize = True  # the device path is always batched
@@ -114,6 +123,8 @@ class EnsembleSampler(object):
         self._pinned = None
         if pinned_results:
             self._pinned = (_lib.pinned_empty((self.nwalkers, self.ndim)), _lib.pinned_empty((self.nwalkers,)))
+        self._rdv = None  # multi-GPU: the host rendezvous this sampler is attached to (``attach``)
+        self._gather_results = True
 
         self.backend = Backend() if backend is None else backend
         if not self.backend.initialized:  # ensemble.py:137-141
@@ -169,6 +180,7 @@ class EnsembleSampler(object):
         d["_saved_pinned"] = self._pinned is not None
         for k in ("_engine", "_random", "_pinned"):
             d.pop(k, None)
+        d["_rdv"] = None  # a communicator does not survive pickling: re-attach after loading
         d["pool"] = None
         return d
 
@@ -183,6 +195,46 @@ class EnsembleSampler(object):
         self._pinned = None
         if pinned:
             self._pinned = (_lib.pinned_empty((self.nwalkers, self.ndim)), _lib.pinned_empty((self.nwalkers,)))
+
+    # ------------------------------------------------------------ multi-GPU
+    def attach(self, rdv, mode="p2p", gather_results=True):
+        """Shard the ensemble by row block over the ranks of ``rdv``
+        (:class:`emcee_b200.dist.Rendezvous`; one process per GPU, every rank
+        builds the same sampler with the same seed and calls the same methods).
+
+        ``gather_results=True``: yielded / returned states hold every walker
+        (one collective replication per read-back).  ``False``: only the rows
+        this rank owns (``owned_rows``) cross PCIe -- the other rows of the
+        returned arrays are not refreshed."""
+        from . import dist
+
+        dist.attach(self._engine, rdv, mode)
+        self._rdv = rdv
+        self._gather_results = bool(gather_results)
+
+    @property
+    def owned_rows(self):
+        """``slice`` of the walkers this process updates (all of them on one GPU)."""
+        r0, n = self._engine.owned_rows()
+        return slice(r0, r0 + n)
+
+    def enable_moments(self, every=1):
+        """Accumulate the chain mean / covariance on the device after every
+        ``every``-th step (``0`` disables; calling it resets the accumulators)."""
+        self._engine.set_option("moments_every", int(every))
+
+    def moments(self):
+        """``(mean[ndim], cov[ndim, ndim], count)`` over the ``(step, walker)``
+        samples accumulated since :meth:`enable_moments` -- what
+        ``np.mean`` / ``np.cov(rowvar=False)`` of ``get_chain(flat=True)`` give,
+        without storing or downloading the chain (``store=False`` runs,
+        ``ensemble.py:287-291``).  Collective on a sharded ensemble."""
+        from . import dist
+
+        part = self._engine.moments()
+        parts = [part] if self._rdv is None else self._rdv.allgather(part)
+        mean, cov, n, _ = dist.combine_moments(parts)
+        return mean, cov, n
 
     # ------------------------------------------------------------- the driver
     def _schedule(self):
@@ -231,7 +283,7 @@ class EnsembleSampler(object):
             raise ValueError("incompatible input dimensions {0}".format(state_shape))
         if state.blobs is not None:
             raise NotImplementedError("blobs are not supported on the device path")
-        if (not skip_initial_state_check) and (not walkers_independent(state.coords)):
+        if (not skip_initial_state_check) and (not self._walkers_independent(state.coords)):
             raise ValueError(
                 "Initial state has a large condition number. "
                 "Make sure that your walkers are linearly independent for the "
@@ -264,10 +316,13 @@ class EnsembleSampler(object):
         eng = self._engine
 
         def refresh():
-            if self._pinned is not None:
-                state.coords, state.log_prob = eng.get_state(*self._pinned)
+            bufs = self._pinned if self._pinned is not None else (
+                np.empty((self.nwalkers, self.ndim)), np.empty(self.nwalkers))
+            if self._rdv is not None and not self._gather_results:
+                r0, n = eng.owned_rows()  # sharded: only the owned block crosses PCIe
+                state.coords, state.log_prob = eng.get_state_rows(r0, n, *bufs)
             else:
-                state.coords, state.log_prob = eng.get_state()
+                state.coords, state.log_prob = eng.get_state(*bufs)
             state.random_state = self.random_state
 
         if _bulk and iterations is not None and (not store or (native_store and thin is None)):
@@ -326,6 +381,25 @@ class EnsembleSampler(object):
             pass
         self._previous_state = results
         return results
+
+    def _walkers_independent(self, coords):
+        """``walkers_independent`` (``ensemble.py:653-663``) with the O(N D^2) part on
+        the device: ``eb_walkers_gram`` returns ``C^T C`` of the centred,
+        column-normalised walkers, the host solves the ``D x D`` symmetric
+        eigen-problem, ``cond(C) = sqrt(l_max / l_min)``.  Squaring halves the
+        digits, so only a clearly well-conditioned ensemble (cond <= 1e6 by the
+        Gram matrix) is accepted here; anything nearer the reference's 1e8
+        threshold is decided by the reference's own SVD statement on the host."""
+        coords = np.asarray(coords, dtype=np.float64)
+        if coords.ndim != 2 or coords.shape[1] != self.ndim or self.ndim > 1024:
+            return walkers_independent(coords)
+        gram, flags = self._engine.walkers_gram(coords)
+        if flags:
+            return False  # non-finite coordinate or a column without span
+        ev = np.linalg.eigvalsh(gram)
+        if ev[0] > 0 and np.sqrt(ev[-1] / ev[0]) <= 1e6:
+            return True
+        return walkers_independent(coords)
 
     def compute_log_prob(self, coords):
         """``(log_prob, None)`` for ``coords[..., ndim]`` evaluated on the device

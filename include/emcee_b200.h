@@ -96,8 +96,21 @@ int eb_model_set(eb_ctx* ctx, int kind, const double* params, size_t nparams);
  * log_prob == NULL -> evaluated on the device.  Non-finite coords / NaN
  * log-prob give the reference's errors. */
 int eb_set_state(eb_ctx* ctx, const double* coords, const double* log_prob);
-/* device -> host copy of the live state; either pointer may be NULL. */
+/* device -> host copy of the live state; either pointer may be NULL.
+ * Sharded ensembles (after eb_comm_init): eb_set_state reads only the rows this
+ * rank owns from the (globally indexed) host arrays, and eb_get_state returns
+ * the GLOBAL state -- it replicates the other ranks' rows first and is
+ * therefore COLLECTIVE (every rank calls it at the same point), as are
+ * eb_get_naccepted, eb_step with accepted_last != NULL and eb_step_store. */
 int eb_get_state(eb_ctx* ctx, double* coords, double* log_prob);
+/* rows [row0, row0 + nrows) this context owns: the whole ensemble on one GPU,
+ * the rank's row block after eb_comm_init. */
+int eb_owned_rows(const eb_ctx* ctx, int64_t* row0, int64_t* nrows);
+/* device -> host copy of rows [row0, row0 + nrows) of the live state into
+ * coords[nrows * ndim] / log_prob[nrows] (either may be NULL).  Not collective:
+ * on a sharded ensemble only the owned block (or any rows after a collective
+ * read) is valid; other rows are refused with EB_ERR_STATE. */
+int eb_get_state_rows(eb_ctx* ctx, int64_t row0, int64_t nrows, double* coords, double* log_prob);
 
 /* ---- log-probability (ensemble.py:458-553) ------------------------------ */
 /* EnsembleSampler.compute_log_prob(coords[m, ndim]) -> out[m], with the
@@ -135,6 +148,24 @@ int eb_step_store(eb_ctx* ctx, const eb_move* moves, size_t nmoves, uint64_t nst
 int eb_get_naccepted(eb_ctx* ctx, uint64_t* naccepted);
 int eb_reset_counters(eb_ctx* ctx);
 
+/* ---- chain analysis on the device --------------------------------------- */
+/* Running moments of the chain for store=False runs (ensemble.py:287-291 keeps
+ * nothing; a caller who wants the chain mean / covariance would otherwise need
+ * a D2H of the state every step).  Enabled by eb_set_option("moments_every", n):
+ * after every n-th step the rows this context owns are folded into device
+ * accumulators (sum and outer-product sum on the FP64 tensor pipe).  Returns
+ * mean[ndim], cov[ndim*ndim] (= np.mean / np.cov(rowvar=False, ddof=1) over
+ * the accumulated (step, walker) samples), their number, and the total number
+ * of accepted proposals of the owned walkers; any output may be NULL.  On a
+ * sharded ensemble the values are per rank (the host combines them). */
+int eb_moments(eb_ctx* ctx, double* mean, double* cov, uint64_t* count, uint64_t* naccepted_total);
+/* walkers_independent (ensemble.py:653-663) on the device: gram[ndim*ndim] =
+ * C^T C of the centred, column-normalised coords[rows, ndim] (:656-661), whose
+ * extreme eigenvalues give cond(C)^2.  *flags: bit 0 = non-finite coordinate
+ * (:655), bit 1 = a column with zero span (:659-660).  The D x D symmetric
+ * eigen-solve stays on the host (numpy). */
+int eb_walkers_gram(eb_ctx* ctx, const double* coords, size_t rows, double* gram, int* flags);
+
 /* ---- measurement / test taps ------------------------------------------- */
 /* device time (ms, CUDA events on the engine's stream) of the last eb_step /
  * eb_step_store call, first launch to last, and the number of kernels it
@@ -156,7 +187,9 @@ int eb_debug_timeline(eb_ctx* ctx, int64_t* out, size_t capacity, size_t* writte
  * for the HBM-bound models; default 1), "dmma_stagger" (0/1: staggered
  * first tiles at launch start; default 1), "dmma_group" (n >= 1: half-steps
  * fused into one persistent cooperative launch of that kernel, separated by an
- * in-kernel grid barrier; default 1), "dmma_timeline" (0/1: record consumer cycle stamps
+ * in-kernel grid barrier -- and, on a P2P-sharded ensemble, a peer-flag barrier; default 1), "pdl" (0/1: consecutive dense_dmma launches chain as programmatic
+ * dependent launches so a launch's prologue overlaps its predecessor's tail; default 1), "moments_every" (n >= 0: see
+ * eb_moments; setting it resets the accumulators), "dmma_timeline" (0/1: record consumer cycle stamps
  * for eb_debug_timeline), "l2_flush"
  * (0/1: benchmark hygiene -- write a 256 MiB buffer before every step and time
  * each step with its own CUDA-event pair, so eb_last_step_timing excludes the

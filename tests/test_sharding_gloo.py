@@ -30,7 +30,8 @@ def _moves(rb, spec):
 
 def _worker(rank, world, port, cases, out):
     sys.path.insert(0, ROOT)
-    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                      EB_RDV_FILE=out % (99, 99) + ".rdv")
     import torch
     import torch.distributed as td
 
@@ -38,7 +39,13 @@ def _worker(rank, world, port, cases, out):
     from oracle import redblue as rb
     from oracle import targets as T
 
-    rdv = dist.Rendezvous("gloo")
+    td.init_process_group("gloo", rank=rank, world_size=world)  # the emulated data-path collective
+    # the product's own host rendezvous (TCP star, no torch): exercise its collectives as well
+    rdv = dist.Rendezvous()
+    assert rdv.allgather(("r", rank)) == [("r", r) for r in range(world)]
+    assert rdv.bcast(b"id-%d" % rank, src=0) == b"id-0"
+    assert rdv.max(10.0 + rank) == 10.0 + world - 1
+    rdv.barrier()
     for ci, (name, N, D, moves, steps) in enumerate(cases):
         target, p0 = T.make_config(name, N, D)
         o = rb.OracleSampler(N, D, target, _moves(rb, moves), seed=77)
@@ -60,6 +67,7 @@ def _worker(rank, world, port, cases, out):
         o.run(steps)
         np.savez(out % (ci, rank), coords=o.coords, log_prob=o.log_prob)
     rdv.close()
+    td.destroy_process_group()
 
 
 CASES = [
