@@ -79,6 +79,7 @@ _SIGNATURES = {
     "eb_reset_counters": (C.c_int, [C.c_void_p]),
     "eb_moments": (C.c_int, [C.c_void_p, _dp, _dp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "eb_walkers_gram": (C.c_int, [C.c_void_p, _dp, C.c_size_t, _dp, C.POINTER(C.c_int)]),
+    "eb_autocorr": (C.c_int, [C.c_void_p, _dp, C.c_size_t, C.c_size_t, C.c_size_t, _dp]),
     "eb_last_step_timing": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_uint64)]),
     "eb_debug_taps": (
         C.c_int,
@@ -264,6 +265,17 @@ class Engine(object):
         flags = C.c_int()
         self._check(lib().eb_walkers_gram(self._h, _as_dp(coords), coords.shape[0], _as_dp(gram), C.byref(flags)))
         return gram, int(flags.value)
+
+    def autocorr_function(self, chain):
+        """Walker-averaged normalised autocorrelation function ``[n_step, n_param]`` of
+        ``chain[n_step, n_walker, n_param]`` (``eb_autocorr``)."""
+        chain = _f64(chain)
+        if chain.ndim != 3:
+            raise ValueError("invalid dimensions")
+        n_t, n_w, n_d = chain.shape
+        out = np.empty((n_d, n_t), dtype=np.float64)
+        self._check(lib().eb_autocorr(self._h, _as_dp(chain), n_t, n_w, n_d, _as_dp(out)))
+        return np.ascontiguousarray(out.T)
 
     def compute_log_prob(self, coords):
         coords = _f64(coords)

@@ -43,11 +43,15 @@ def function_1d(x):
     return _acf(np.asarray(x, dtype=np.float64))
 
 
-def integrated_time(x, c=5, tol=50, quiet=False, has_walkers=True):
+def integrated_time(x, c=5, tol=50, quiet=False, has_walkers=True, engine=None):
     """``tau[n_param]`` for ``x[n_step]``, ``x[n_step, n_walker]`` (or
     ``[n_step, n_param]`` with ``has_walkers=False``) or ``x[n_step, n_walker,
     n_param]``; raises :class:`AutocorrError` (or warns when ``quiet``) if the
-    chain is shorter than ``tol`` autocorrelation times."""
+    chain is shorter than ``tol`` autocorrelation times.
+
+    ``engine`` (an ``_lib.Engine``): evaluate the walker-averaged
+    autocorrelation functions on the GPU (``eb_autocorr``: hand-written
+    batched FFTs) instead of ``numpy.fft``; the window search below is the same."""
     x = np.atleast_1d(np.asarray(x, dtype=np.float64))
     if x.ndim == 1:
         x = x[:, None, None]
@@ -56,7 +60,10 @@ def integrated_time(x, c=5, tol=50, quiet=False, has_walkers=True):
     if x.ndim != 3:
         raise ValueError("invalid dimensions")
     n_t, n_w, n_d = x.shape
-    rho = np.mean(_acf(x), axis=1)  # [n_t, n_d], walker-averaged
+    if engine is not None:
+        rho = engine.autocorr_function(x)  # [n_t, n_d], walker-averaged on the device
+    else:
+        rho = np.mean(_acf(x), axis=1)  # [n_t, n_d], walker-averaged
     taus = 2.0 * np.cumsum(rho, axis=0) - 1.0
     lags = np.arange(n_t)[:, None]
     inside = lags < c * taus  # Sokal: smallest M with M >= c * tau(M)

@@ -166,6 +166,139 @@ __global__ void moments_reduce_kernel(const double* __restrict__ partial, int np
   acc[e] += s;
 }
 
+// ===========================================================================
+// walker-averaged normalised autocorrelation function of a stored chain (autocorr.py:21-46, 101-107)
+// ===========================================================================
+// Per series (walker, parameter): x - mean, zero-padded to M = 2 * next_pow_two(n_t); forward FFT,
+// |F|^2, inverse FFT, acf / acf[0].  The transform is an in-place radix-2 pair that needs no
+// bit-reversal pass: decimation-in-frequency forward (natural in, bit-reversed out), the pointwise
+// power spectrum (order-agnostic), decimation-in-time inverse (bit-reversed in, natural out).
+// Butterflies of span h < ACF_BLOCK / 2 stay inside aligned blocks of ACF_BLOCK points and run in
+// shared memory (one CTA per block: all small-span forward stages, the power spectrum and all
+// small-span inverse stages in one pass); larger spans are one global-memory pass each.
+constexpr int ACF_BLOCK = 8192;  // 128 KB of double2 in shared memory
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// tw[k] = exp(-2 pi i k / M), k < M / 2
+__global__ void acf_twiddle_kernel(double2* __restrict__ tw, int M) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= M / 2) return;
+  double sn, cs;
+  sincospi(-2.0 * (double)k / (double)M, &sn, &cs);
+  tw[k] = make_double2(cs, sn);
+}
+
+// xin[n_t][S] (series contiguous) -> mean[S]; one thread per series, fixed order over t
+__global__ void acf_mean_kernel(const double* __restrict__ xin, int n_t, int S, double* __restrict__ mean) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double acc = 0.0;
+  for (int t = 0; t < n_t; ++t) acc += xin[(size_t)t * S + s];
+  mean[s] = acc / (double)n_t;
+}
+
+// z[s][t] = (xin[t][s] - mean[s], 0) for t < n_t, 0 beyond: 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) acf_load_kernel(const double* __restrict__ xin, const double* __restrict__ mean,
+                                                       int n_t, int S, int M, double2* __restrict__ z) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int t0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+  for (int y = ty; y < 32; y += 8) {
+    const int t = t0 + y, s = s0 + tx;
+    tile[y][tx] = (t < n_t && s < S) ? xin[(size_t)t * S + s] - mean[s] : 0.0;
+  }
+  __syncthreads();
+  for (int y = ty; y < 32; y += 8) {
+    const int s = s0 + y, t = t0 + tx;
+    if (s < S && t < M) z[(size_t)s * M + t] = make_double2(tile[tx][y], 0.0);
+  }
+}
+
+// one butterfly stage of span h over every series (global memory): forward = DIF, inverse = DIT
+__global__ void fft_global_stage_kernel(double2* __restrict__ z, const double2* __restrict__ tw, int S, int M, int h,
+                                        int inverse) {
+  const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t half = (size_t)M / 2;
+  if (id >= (size_t)S * half) return;
+  const size_t s = id / half;
+  const int b = (int)(id - s * half);
+  const int j = b & (h - 1);
+  const int i = ((b - j) << 1) + j;
+  double2* x = z + s * M;
+  double2 w = tw[(size_t)j * (M / (2 * h))];
+  const double2 u = x[i], v = x[i + h];
+  if (!inverse) {
+    x[i] = make_double2(u.x + v.x, u.y + v.y);
+    x[i + h] = cmul(make_double2(u.x - v.x, u.y - v.y), w);
+  } else {
+    w.y = -w.y;
+    const double2 vw = cmul(v, w);
+    x[i] = make_double2(u.x + vw.x, u.y + vw.y);
+    x[i + h] = make_double2(u.x - vw.x, u.y - vw.y);
+  }
+}
+
+// grid (M / B, S): the stages of span < B of one aligned block of B points, in shared memory
+__global__ void __launch_bounds__(512) fft_local_kernel(double2* __restrict__ z, const double2* __restrict__ tw, int M,
+                                                        int B) {
+  extern __shared__ double2 sz[];
+  double2* base = z + (size_t)blockIdx.y * M + (size_t)blockIdx.x * B;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) sz[i] = base[i];
+  for (int h = B / 2; h >= 1; h >>= 1) {  // forward, decimation in frequency
+    __syncthreads();
+    const int tstep = M / (2 * h);
+    for (int b = threadIdx.x; b < B / 2; b += blockDim.x) {
+      const int j = b & (h - 1);
+      const int i = ((b - j) << 1) + j;
+      const double2 u = sz[i], v = sz[i + h];
+      sz[i] = make_double2(u.x + v.x, u.y + v.y);
+      sz[i + h] = cmul(make_double2(u.x - v.x, u.y - v.y), tw[(size_t)j * tstep]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {  // power spectrum (autocorr.py:43-44)
+    const double2 v = sz[i];
+    sz[i] = make_double2(v.x * v.x + v.y * v.y, 0.0);
+  }
+  for (int h = 1; h <= B / 2; h <<= 1) {  // inverse, decimation in time
+    __syncthreads();
+    const int tstep = M / (2 * h);
+    for (int b = threadIdx.x; b < B / 2; b += blockDim.x) {
+      const int j = b & (h - 1);
+      const int i = ((b - j) << 1) + j;
+      double2 w = tw[(size_t)j * tstep];
+      w.y = -w.y;
+      const double2 u = sz[i], vw = cmul(sz[i + h], w);
+      sz[i] = make_double2(u.x + vw.x, u.y + vw.y);
+      sz[i + h] = make_double2(u.x - vw.x, u.y - vw.y);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x) base[i] = sz[i];
+}
+
+// f[d][lag] += sum over the slab's walkers (ascending) of acf[(w, d)][lag] / acf[(w, d)][0]   (autocorr.py:45,105)
+__global__ void acf_accumulate_kernel(const double2* __restrict__ z, int wb, int nd, int n_t, int M,
+                                      double* __restrict__ f) {
+  const int lag = blockIdx.x * blockDim.x + threadIdx.x;
+  const int d = blockIdx.y;
+  if (lag >= n_t) return;
+  double acc = 0.0;
+  for (int w = 0; w < wb; ++w) {
+    const double2* x = z + (size_t)(w * nd + d) * M;
+    acc += x[lag].x / x[0].x;
+  }
+  f[(size_t)d * n_t + lag] += acc;
+}
+
+__global__ void acf_scale_kernel(double* __restrict__ f, size_t n, double scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f[i] *= scale;
+}
+
 }  // namespace
 
 // ---- host-side launchers -----------------------------------------------------------------
@@ -213,6 +346,47 @@ cudaError_t launch_moments(const double* X, int64_t nrows, int D, const double* 
   if (e != cudaSuccess) return e;
   const size_t n = (size_t)D + (size_t)D * D;
   moments_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, grid, D, acc);
+  return cudaGetLastError();
+}
+
+
+// ---- autocorrelation -------------------------------------------------------------------------
+int acf_fft_length(size_t n_t) {
+  size_t n = 1;
+  while (n < n_t) n <<= 1;  // autocorr.py:12-17 next_pow_two
+  return (int)(2 * n);
+}
+
+// bytes of device scratch per series of the slab: complex work array + its row of the chain slab
+size_t acf_bytes_per_series(size_t n_t) { return (size_t)acf_fft_length(n_t) * sizeof(double2) + n_t * sizeof(double); }
+
+cudaError_t launch_acf_twiddles(double2* tw, int M, cudaStream_t st) {
+  acf_twiddle_kernel<<<(M / 2 + 255) / 256, 256, 0, st>>>(tw, M);
+  return cudaGetLastError();
+}
+
+// One slab: xin[n_t][S = wb * nd] (device) -> f[nd][n_t] += sum over the slab's walkers of the normalised
+// autocorrelation functions.  z: S * M complex scratch, mean: S doubles.
+cudaError_t launch_acf_slab(const double* xin, int n_t, int wb, int nd, int M, const double2* tw, double2* z,
+                            double* mean, double* f, cudaStream_t st) {
+  const int S = wb * nd;
+  acf_mean_kernel<<<(S + 127) / 128, 128, 0, st>>>(xin, n_t, S, mean);
+  acf_load_kernel<<<dim3((M + 31) / 32, (S + 31) / 32), 256, 0, st>>>(xin, mean, n_t, S, M, z);
+  const int B = M < ACF_BLOCK ? M : ACF_BLOCK;
+  const size_t butterflies = (size_t)S * (M / 2);
+  const unsigned gblocks = (unsigned)((butterflies + 255) / 256);
+  for (int h = M / 2; h >= B; h >>= 1) fft_global_stage_kernel<<<gblocks, 256, 0, st>>>(z, tw, S, M, h, 0);
+  const size_t smem = (size_t)B * sizeof(double2);
+  cudaError_t e = cudaFuncSetAttribute(fft_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  fft_local_kernel<<<dim3(M / B, S), B >= 1024 ? 512 : 128, smem, st>>>(z, tw, M, B);
+  for (int h = B; h <= M / 2; h <<= 1) fft_global_stage_kernel<<<gblocks, 256, 0, st>>>(z, tw, S, M, h, 1);
+  acf_accumulate_kernel<<<dim3((n_t + 255) / 256, nd), 256, 0, st>>>(z, wb, nd, n_t, M, f);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_acf_scale(double* f, size_t n, double scale, cudaStream_t st) {
+  acf_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f, n, scale);
   return cudaGetLastError();
 }
 

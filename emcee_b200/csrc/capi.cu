@@ -1106,6 +1106,59 @@ int eb_walkers_gram(eb_ctx* c, const double* coords, size_t rows, double* gram, 
   return EB_OK;
 }
 
+int eb_autocorr(eb_ctx* c, const double* chain, size_t n_t, size_t nw, size_t nd, double* acf) {
+  if (!c) return EB_ERR_INVALID;
+  if (!chain || !acf || n_t == 0 || nw == 0 || nd == 0) FAIL(c, EB_ERR_INVALID, "eb_autocorr: empty chain or null buffer");
+  if (n_t > ((size_t)1 << 26) || nw * nd > ((size_t)1 << 31))
+    FAIL(c, EB_ERR_UNSUPPORTED, "eb_autocorr: chain too long (n_step <= 2^26)");
+  CK(c, cudaSetDevice(c->device));
+  const int M = acf_fft_length(n_t);
+  // slab of walkers sized to ~1 GiB of scratch (at least one walker)
+  const size_t per_walker = acf_bytes_per_series(n_t) * nd;
+  size_t wb = ((size_t)1 << 30) / per_walker;
+  wb = std::max<size_t>(1, std::min(wb, nw));
+  const size_t S = wb * nd;
+  double *xin = nullptr, *mean = nullptr, *f = nullptr;
+  double2 *z = nullptr, *tw = nullptr;
+  auto release = [&]() {
+    cudaFree(xin);
+    cudaFree(mean);
+    cudaFree(f);
+    cudaFree(z);
+    cudaFree(tw);
+  };
+#define AC(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      cudaGetLastError();                                                                    \
+      release();                                                                             \
+      FAIL(c, EB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    }                                                                                        \
+  } while (0)
+  AC(cudaMalloc(&xin, n_t * S * sizeof(double)));
+  AC(cudaMalloc(&mean, S * sizeof(double)));
+  AC(cudaMalloc(&f, nd * n_t * sizeof(double)));
+  AC(cudaMalloc(&z, S * (size_t)M * sizeof(double2)));
+  AC(cudaMalloc(&tw, (size_t)std::max(1, M / 2) * sizeof(double2)));
+  c->chain_ok = false;
+  AC(cudaMemsetAsync(f, 0, nd * n_t * sizeof(double), c->st));
+  AC(launch_acf_twiddles(tw, M, c->st));
+  for (size_t w0 = 0; w0 < nw; w0 += wb) {
+    const size_t wn = std::min(wb, nw - w0);
+    // chain[t][w0 .. w0 + wn)[:] -> xin[t][wn * nd]: one strided copy (rows of the slab are contiguous in a step)
+    AC(cudaMemcpy2DAsync(xin, wn * nd * sizeof(double), chain + w0 * nd, nw * nd * sizeof(double),
+                         wn * nd * sizeof(double), n_t, cudaMemcpyHostToDevice, c->st));
+    AC(launch_acf_slab(xin, (int)n_t, (int)wn, (int)nd, M, tw, z, mean, f, c->st));
+  }
+  AC(launch_acf_scale(f, nd * n_t, 1.0 / (double)nw, c->st));  // autocorr.py:106  f /= n_w
+  AC(cudaMemcpyAsync(acf, f, nd * n_t * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  AC(cudaStreamSynchronize(c->st));
+#undef AC
+  release();
+  return EB_OK;
+}
+
 int eb_last_step_timing(const eb_ctx* c, double* ms, uint64_t* launches) {
   if (!c) return EB_ERR_INVALID;
   if (ms) *ms = c->last_ms;

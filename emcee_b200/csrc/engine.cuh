@@ -118,6 +118,14 @@ size_t moments_partial_bytes(int D, int sm_count);
 cudaError_t launch_moments(const double* X, int64_t nrows, int D, const double* shift, double* partial, double* acc,
                            int sm_count, cudaStream_t st);
 
+// walker-averaged normalised autocorrelation function (autocorr.py:21-46,101-107), slab by slab
+int acf_fft_length(size_t n_t);
+size_t acf_bytes_per_series(size_t n_t);
+cudaError_t launch_acf_twiddles(double2* tw, int M, cudaStream_t st);
+cudaError_t launch_acf_slab(const double* xin, int n_t, int wb, int nd, int M, const double2* tw, double2* z,
+                            double* mean, double* f, cudaStream_t st);
+cudaError_t launch_acf_scale(double* f, size_t n, double scale, cudaStream_t st);
+
 inline int lanes_per_walker(int D) {
   int g = 4;
   while (g < 32 && g * 4 < D) g <<= 1;

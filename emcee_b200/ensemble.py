@@ -427,8 +427,13 @@ class EnsembleSampler(object):
     def get_value(self, name, **kwargs):
         return self.backend.get_value(name, **kwargs)
 
-    def get_autocorr_time(self, **kwargs):
-        return self.backend.get_autocorr_time(**kwargs)
+    def get_autocorr_time(self, discard=0, thin=1, **kwargs):
+        """Integrated autocorrelation time of the stored chain (``ensemble.py:619-623``
+        -> ``backends/backend.py:130-150``), the FFTs on the GPU (``eb_autocorr``)."""
+        from . import autocorr
+
+        x = self.get_chain(discard=discard, thin=thin)
+        return thin * autocorr.integrated_time(x, engine=self._engine, **kwargs)
 
 
 def walkers_independent(coords):

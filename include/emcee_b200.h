@@ -165,6 +165,15 @@ int eb_moments(eb_ctx* ctx, double* mean, double* cov, uint64_t* count, uint64_t
  * (:655), bit 1 = a column with zero span (:659-660).  The D x D symmetric
  * eigen-solve stays on the host (numpy). */
 int eb_walkers_gram(eb_ctx* ctx, const double* coords, size_t rows, double* gram, int* flags);
+/* The device part of autocorr.integrated_time (autocorr.py:49-123, called from
+ * backends/backend.py:130-150 on the stored chain): for chain[n_step, n_walker,
+ * n_param] (host, C order) acf[n_param, n_step] = the walker average of the
+ * normalised autocorrelation functions function_1d(chain[:, k, d])
+ * (autocorr.py:21-46: FFT of the mean-subtracted series zero-padded to
+ * 2*next_pow_two(n_step), power spectrum, inverse FFT, / acf[0]; :101-106).
+ * Sokal's window search on acf (:107-109) is O(n_step * n_param) and stays
+ * on the host.  Independent of the context's ensemble shape. */
+int eb_autocorr(eb_ctx* ctx, const double* chain, size_t n_step, size_t n_walker, size_t n_param, double* acf);
 
 /* ---- measurement / test taps ------------------------------------------- */
 /* device time (ms, CUDA events on the engine's stream) of the last eb_step /

@@ -154,3 +154,63 @@ def test_host_moves_are_rejected_up_front():
         emcee_b200.EnsembleSampler(8, 2, models.GaussianIso(), moves=HostMove())
     with pytest.raises(TypeError, match="device moves"):
         emcee_b200.EnsembleSampler(8, 2, models.GaussianIso(), moves=[(moves.StretchMove(), 0.5), (HostMove(), 0.5)])
+
+
+# ---- autocorrelation on the device (autocorr.py:49-123) ---------------------------------------------
+import os  # noqa: E402
+
+from emcee_b200 import autocorr  # noqa: E402
+
+_FIX = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures", "autocorr_reference.npz"))
+
+
+def _ar1_chain(seed, n, w, d):
+    rng = np.random.default_rng(seed)
+    x = np.empty((n, w, d))
+    x[0] = 0
+    e = rng.random((n, w, d))
+    for i in range(1, n):
+        x[i] = x[i - 1] * 0.9 + e[i]
+    return x
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_device_autocorr_matches_reference_fixture(name):
+    """tau from the GPU FFTs vs the values the UNMODIFIED reference computed for the same seeded AR(1)
+    chains (tests/fixtures/autocorr_reference.npz, oracle/gen_autocorr_fixture.py).  FFT lengths
+    16 384 .. 131 072: shared-memory stages plus the global-memory large-span passes."""
+    seed, n, w, d = (int(v) for v in _FIX["cfg_" + name])
+    s = emcee_b200.EnsembleSampler(8, 2, models.GaussianIso(), seed=1)
+    x = _ar1_chain(seed, n, w, d)
+    tau = autocorr.integrated_time(x, quiet=True, engine=s._engine)
+    np.testing.assert_allclose(tau, _FIX["tau_" + name], rtol=1e-8)
+    rho_dev = s._engine.autocorr_function(x)
+    rho_host = np.mean(autocorr._acf(x), axis=1)
+    np.testing.assert_allclose(rho_dev, rho_host, rtol=0, atol=2e-10)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 3, 2), (37, 5, 3), (1000, 64, 5), (3000, 2, 2), (4096, 3, 1), (4097, 2, 2)])
+def test_device_autocorr_function_small_and_odd_lengths(shape):
+    n, w, d = shape
+    s = emcee_b200.EnsembleSampler(8, 2, models.GaussianIso(), seed=1)
+    x = _ar1_chain(7, n, w, d) if n > 1 else np.ones((1, 1, 1))
+    got = s._engine.autocorr_function(x)
+    want = np.mean(autocorr._acf(x), axis=1)
+    assert got.shape == (n, d)
+    if n == 1:
+        assert np.all(np.isnan(got)) and np.all(np.isnan(want))  # 0 / 0, as numpy gives
+        return
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-10)
+    if shape == (3000, 2, 2):
+        np.testing.assert_allclose(s._engine.autocorr_function(x[:, :1, :1])[:16, 0], _FIX["acf_head"], rtol=1e-9, atol=1e-12)
+
+
+def test_sampler_get_autocorr_time_uses_the_device():
+    g = load_golden("stretch_iso_32x5")
+    s = golden_sampler(g)
+    s.run_mcmc(g["p0"], 60, skip_initial_state_check=True)
+    tau_dev = s.get_autocorr_time(quiet=True)
+    tau_host = autocorr.integrated_time(s.get_chain(), quiet=True)
+    np.testing.assert_allclose(tau_dev, tau_host, rtol=1e-9)
+    with pytest.raises(autocorr.AutocorrError):
+        s.get_autocorr_time()
