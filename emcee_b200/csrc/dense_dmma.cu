@@ -303,18 +303,24 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
           issue(nxt, b ^ 1);
           return true;
         };
+        // own rows of this tile (always local): plain 16-byte loads issued NOW and consumed after the
+        // partner rows have landed -- their latency hides behind the next tile's draws and the wait for
+        // a free landing buffer instead of sitting on the producer's critical path
+        const int32_t wg = __shfl_sync(0xffffffffu, cur.w, g);
+        const double* srow = a.coords + (size_t)wg * D + 2 * t;
+        double2 sreg[KB];
+#pragma unroll
+        for (int j = 0; j < KB; ++j) sreg[j] = __ldcg(reinterpret_cast<const double2*>(srow + 8 * j));
+        const double lp_old = __ldcg(a.logp + cur.w);
         // steady state: the next tile's partner rows are requested BEFORE this tile is processed
         if (has_next && !first && !issue_next()) return;
         // ---- partner rows of this tile have landed: form the proposal over them
         const double zz = __shfl_sync(0xffffffffu, cur.zz, g);
-        const int32_t wg = __shfl_sync(0xffffffffu, cur.w, g);
-        const double* srow = a.coords + (size_t)wg * D + 2 * t;
         double* myC = slot + (size_t)b * SL::buf_doubles + (size_t)g * RS + 2 * t;
-        const double lp_old = __ldcg(a.logp + cur.w);
         if (!mbar_wait_abortable(barFull + b, (k >> 1) & 1u, sAbort)) return;
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
-          const double2 s2 = __ldcg(reinterpret_cast<const double2*>(srow + 8 * j));
+          const double2 s2 = sreg[j];
           const double2 c2 = *reinterpret_cast<const double2*>(myC + 8 * j);
           // stretch.py:33  q = c - (c - s) * zz, each op rounded once (no FMA contraction)
           double2 q2;
