@@ -70,17 +70,34 @@ def case_list(emcee):
         ("mix3_ring_64x4", 64, 4, T.Ring(4),
          [(mv.StretchMove(), 0.5), (mv.DEMove(), 0.3), (mv.DESnookerMove(gammas=1.2), 0.2)],
          p0(64, 4, 2.5), 50),
+        # ---- round 2: WalkMove (walk.py:27-37) and GaussianMove / MHMove (gaussian.py, mh.py:35-65) ----
+        ("walk_all_rosen_40x4", 40, 4, T.Rosenbrock(4), mv.WalkMove(), p0(40, 4, 0.1, 1.0), 40),
+        ("walk_s6_iso_32x5", 32, 5, iso5, mv.WalkMove(s=6), p0(32, 5), 40),
+        ("walk_s3_nsplits3_ring_48x4", 48, 4, T.Ring(4), mv.WalkMove(s=3, nsplits=3), p0(48, 4, 2.5), 30),
+        ("walk_all_dense_64x8", 64, 8, d8, mv.WalkMove(), p0(64, 8), 30),
+        ("gauss_iso_vector_32x5", 32, 5, iso5, mv.GaussianMove(0.3), p0(32, 5), 40),
+        ("gauss_iso_random_factor_rosen_40x4", 40, 4, T.Rosenbrock(4),
+         mv.GaussianMove(0.05, mode="random", factor=2.0), p0(40, 4, 0.1, 1.0), 40),
+        ("gauss_diag_sequential_32x5", 32, 5, iso5,
+         mv.GaussianMove(np.array([0.1, 0.2, 0.3, 0.4, 0.5]), mode="sequential"), p0(32, 5), 40),
+        ("gauss_full_factor_dense_64x8", 64, 8, d8,
+         mv.GaussianMove(0.05 * np.linalg.inv(d8.icov), factor=1.5), p0(64, 8), 40),
+        ("mix_walk_stretch_gauss_ring_64x4", 64, 4, T.Ring(4),
+         [(mv.WalkMove(s=8), 0.4), (mv.StretchMove(), 0.3), (mv.GaussianMove(0.1), 0.2), (mv.WalkMove(), 0.1)],
+         p0(64, 4, 2.5), 50),
     ]
 
 
 def describe_moves(moves):
     """Serialise the move schedule as plain arrays: one row per move
-    (kind, weight, nsplits, randomize, p0, p1) with kind 0/1/2 =
-    stretch/de/snooker; p0,p1 = (a,-) / (sigma, gamma0 or nan) / (gammas,-)."""
+    (kind, weight, nsplits, randomize, p0, p1) with kind 0..4 =
+    stretch/de/snooker/walk/gaussian; p0,p1 = (a,-) / (sigma, gamma0 or nan) / (gammas,-) /
+    (s or nan,-) / (mode 0 vector 1 random 2 sequential, factor or nan).  A GaussianMove's ``cov``
+    argument (scalar, vector or matrix, as given) goes to the extra array ``move<k>_cov``."""
     if not isinstance(moves, list):
         moves = [(moves, 1.0)]
-    rows = []
-    for m, w in moves:
+    rows, extra = [], {}
+    for k, (m, w) in enumerate(moves):
         name = type(m).__name__
         if name == "StretchMove":
             rows.append([0, w, m.nsplits, m.randomize_split, m.a, np.nan])
@@ -89,9 +106,20 @@ def describe_moves(moves):
             rows.append([1, w, m.nsplits, m.randomize_split, m.sigma, g])
         elif name == "DESnookerMove":
             rows.append([2, w, m.nsplits, m.randomize_split, m.gammas, np.nan])
+        elif name == "WalkMove":
+            rows.append([3, w, m.nsplits, m.randomize_split, np.nan if m.s is None else m.s, np.nan])
+        elif name == "GaussianMove":
+            prop = m.get_proposal  # gaussian.py:72-119
+            form = type(prop).__name__
+            mode = {"vector": 0, "random": 1, "sequential": 2}[prop.mode]
+            factor = np.nan if prop._log_factor is None else float(np.exp(prop._log_factor))
+            rows.append([4, w, 1, 0, mode, factor])
+            # recover the user's ``cov`` argument: the proposal objects keep sqrt(cov) (:45,:58) or the matrix (:50)
+            extra["move%d_cov" % k] = np.asarray(prop.scale if form == "_proposal" else np.asarray(prop.scale) ** 2,
+                                                 dtype=np.float64)
         else:
             raise ValueError(name)
-    return np.array(rows, dtype=np.float64)
+    return np.array(rows, dtype=np.float64), extra
 
 
 def model_arrays(target):
@@ -136,13 +164,14 @@ def run_case(emcee, name, nwalkers, ndim, target, moves, p0, nsteps, seed):
         "nwalkers": np.array(nwalkers),
         "ndim": np.array(ndim),
         "seed": np.array(seed, dtype=np.uint64),
-        "moves": describe_moves(moves),
+        "moves": describe_moves(moves)[0],
         "p0": p0,
         "lp0": np.asarray(target(p0), dtype=np.float64),
         "chain": chain,
         "log_prob": lps,
         "accepted": acc,
     }
+    arrays.update(describe_moves(moves)[1])
     arrays.update(model_arrays(target))
     for kind, parts in tr.items():
         arrays["trace_" + kind] = np.concatenate(parts)
@@ -173,7 +202,10 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     emcee = import_reference()
     philox_kat()
+    only = set(sys.argv[1:])
     for idx, case in enumerate(case_list(emcee)):
+        if only and case[0] not in only:
+            continue
         run_case(emcee, *case, seed=0x656D636565B200 + idx)
 
 

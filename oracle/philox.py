@@ -43,6 +43,12 @@ __all__ = [
     "TAG_PROP_A",
     "TAG_PROP_B",
     "TAG_ACCEPT",
+    "TAG_NORMAL",
+    "TAG_SUBSET",
+    "sub_split",
+    "normals",
+    "subset_indices",
+    "chol_psd",
 ]
 
 PHILOX_M0 = np.uint64(0xD2511F53)
@@ -57,6 +63,8 @@ TAG_SHUFFLE = 2  # round keys of the split permutation       (red_blue.py:79-80)
 TAG_PROP_A = 3  # first proposal draw block of active rank i
 TAG_PROP_B = 4  # second proposal draw block of active rank i
 TAG_ACCEPT = 5  # Metropolis uniform of active rank i        (red_blue.py:100)
+TAG_NORMAL = 6  # bulk standard normals of row i: block k holds normals 2k, 2k+1 (walk.py:36, gaussian.py:97)
+TAG_SUBSET = 7  # round keys of the helper-subset permutation of active rank i (walk.py:34)
 
 FEISTEL_ROUNDS = 8
 
@@ -141,6 +149,47 @@ def box_muller(u1, u2):
     return np.sqrt(-2.0 * np.log(1.0 - u1)) * np.cos(6.283185307179586 * u2)
 
 
+def sub_split(split, k):
+    """The 24-bit ``split`` field of the counter when a draw block needs one more index: the split
+    number in the low 6 bits (MAX_SPLITS = 32), the sub-index ``k`` (< 2**18) above."""
+    return (int(split) & 0x3F) | (int(k) << 6)
+
+
+def normals(seed, step, split, index, count):
+    """``[len(index), count]`` standard normals: normals ``2k`` and ``2k+1`` of row ``i`` are the cosine
+    and sine branches of the Box-Muller pair of block ``(index=i, sub-index=k, TAG_NORMAL)``."""
+    index = np.atleast_1d(np.asarray(index, dtype=np.uint64))
+    out = np.empty((len(index), int(count)), dtype=np.float64)
+    for k in range((int(count) + 1) // 2):
+        w0, w1, w2, w3 = draw_words(seed, step, sub_split(split, k), TAG_NORMAL, index)
+        r = np.sqrt(-2.0 * np.log(1.0 - u53(w0, w1)))
+        th = 6.283185307179586 * u53(w2, w3)
+        out[:, 2 * k] = r * np.cos(th)
+        if 2 * k + 1 < count:
+            out[:, 2 * k + 1] = r * np.sin(th)
+    return out
+
+
+def chol_psd(cov):
+    """Lower factor ``L`` with ``L L^T = cov`` for a positive SEMI-definite matrix: plain column
+    Cholesky in which a pivot at or below ``1e-12 * max(diag)`` zeroes its column (for a PSD matrix the
+    rest of that column is zero as well).  This is the factorisation the draw specification fixes for
+    ``multivariate_normal(mean, cov) := mean + L z`` (numpy's own uses an SVD whose sign / ordering
+    conventions cannot be reproduced bit-for-bit by independent hardware)."""
+    a = np.atleast_2d(np.asarray(cov, dtype=np.float64))
+    n = a.shape[0]
+    L = np.zeros_like(a)
+    tol = 1e-12 * max(float(np.max(np.diag(a))), 0.0)
+    for j in range(n):
+        d = a[j, j] - np.dot(L[j, :j], L[j, :j])
+        if not d > tol:
+            continue
+        L[j, j] = np.sqrt(d)
+        if j + 1 < n:
+            L[j + 1 :, j] = (a[j + 1 :, j] - L[j + 1 :, :j] @ L[j, :j]) / L[j, j]
+    return L
+
+
 # --------------------------------------------------------------------------
 # split permutation: a keyed bijection on [0, N) that can be evaluated for one
 # element independently of all others (Feistel network + cycle walking; cf.
@@ -165,6 +214,37 @@ def feistel_keys(seed, step):
 def _half_bits(n):
     bits = max(int(n - 1).bit_length(), 2)
     return (bits + 1) // 2
+
+
+def subset_indices(seed, step, split, i, n, count):
+    """``choice(n, count, replace=False)`` of active rank ``i`` (walk.py:34): the first ``count`` images
+    of the Feistel permutation of ``[0, n)`` keyed by blocks ``(index=i, sub-index 0..1, TAG_SUBSET)``;
+    ``count == n`` is defined as the identity order (the covariance does not depend on the order)."""
+    n, count = int(n), int(count)
+    if count == n:
+        return np.arange(n, dtype=np.int64)
+    ws = [draw_words(seed, step, sub_split(split, k), TAG_SUBSET, np.array([i])) for k in range(FEISTEL_ROUNDS // 4)]
+    keys = np.array([int(w[j][0]) for w in ws for j in range(4)], dtype=np.uint64)
+    return _feistel_apply(np.arange(count, dtype=np.uint64), n, keys)
+
+
+def _feistel_apply(x, n, keys):
+    h = np.uint64(_half_bits(n))
+    mask = (np.uint64(1) << h) - np.uint64(1)
+
+    def enc(x):
+        left, right = x >> h, x & mask
+        for r in range(FEISTEL_ROUNDS):
+            left, right = right, left ^ (_fmix32(right ^ keys[r]) & mask)
+        return (left << h) | right
+
+    x = enc(np.asarray(x, dtype=np.uint64))
+    while True:
+        bad = x >= np.uint64(n)
+        if not bad.any():
+            break
+        x[bad] = enc(x[bad])
+    return x.astype(np.int64)
 
 
 def split_permutation(seed, step, n):
@@ -262,6 +342,13 @@ class PhiloxRandom(object):
 
     # -- the seven methods -------------------------------------------------
     def choice(self, a, size=None, replace=True, p=None):
+        if isinstance(a, (int, np.integer)) and not replace:
+            # WalkMove: ``random.choice(Nc, s0, replace=False)`` once per active walker  (walk.py:34)
+            assert p is None
+            self._open_split()
+            out = subset_indices(self.seed, self._cur, self._split, self._i, int(a), int(size))
+            self._log("walk_subset", out.copy())
+            return out
         if isinstance(a, (int, np.integer)):
             # DEMove: ``random.choice(nc*(nc-1), size=ns, replace=True)``  (de.py:49)
             assert replace and p is None
@@ -299,7 +386,40 @@ class PhiloxRandom(object):
         self._i += 1
         self._k = 0
 
+    def multivariate_normal(self, mean, cov):
+        mean = np.asarray(mean, dtype=np.float64)
+        L = chol_psd(cov)
+        if self._phase in ("step", "mh"):
+            # GaussianMove with a full covariance: ONE draw per step, added to every walker (gaussian.py:116-118)
+            self._phase = "mh"
+            z = normals(self.seed, self._cur, 0, np.array([0]), len(mean))[0]
+            self._log("mh_mvn", z.copy())
+            return mean + L @ z
+        # WalkMove: ``random.multivariate_normal(s[i], cov)`` for active rank i  (walk.py:36)
+        assert self._phase == "proposal"
+        z = normals(self.seed, self._cur, self._split, np.array([self._i]), len(mean))[0]
+        self._log("walk_z", z.copy())
+        self._i += 1
+        return mean + L @ z
+
+    def uniform(self, low, high):
+        # GaussianMove ``factor``: ``rng.uniform(-log f, log f)`` once per step  (gaussian.py:91)
+        assert self._phase in ("step", "mh")
+        self._phase = "mh"
+        w0, w1, _, _ = draw_words(self.seed, self._cur, 0, TAG_MOVE, np.array([1]))
+        u = float(u53(w0, w1)[0])
+        self._log("mh_factor", u)
+        return low + (high - low) * u
+
     def rand(self, *shape):
+        if len(shape) == 1 and self._phase == "mh":
+            # MHMove accept draws: ``model.random.rand(nwalkers)``  (mh.py:58)
+            (n,) = shape
+            w0, w1, _, _ = draw_words(self.seed, self._cur, 0, TAG_ACCEPT, np.arange(n))
+            out = u53(w0, w1)
+            self._log("u_accept_mh", out.copy())
+            self._phase = "idle"
+            return out
         if len(shape) == 0:
             # accept draw (red_blue.py:100)
             if self._phase == "proposal":
@@ -320,6 +440,13 @@ class PhiloxRandom(object):
 
     def randint(self, low, high=None, size=None):
         assert high is None
+        if self._phase == "mh":
+            # GaussianMove mode="random": ``rng.randint(ndim, size=nw)``  (gaussian.py:100)
+            n = int(size)
+            w0, w1, _, _ = draw_words(self.seed, self._cur, 0, TAG_PROP_B, np.arange(n))
+            out = bounded64(w0, w1, int(low))
+            self._log("mh_dim", out.copy())
+            return out
         if size is None:
             # DESnookerMove: ``random.randint(Nc[j])`` for j = 0, 1, 2
             # (de_snooker.py:38)
@@ -345,6 +472,13 @@ class PhiloxRandom(object):
         return out
 
     def randn(self, *shape):
+        if self._phase in ("step", "mh"):
+            # GaussianMove: ``rng.randn(nwalkers, ndim)`` -- normal (w, d) of row w  (gaussian.py:97)
+            self._phase = "mh"
+            nw, nd = shape
+            out = normals(self.seed, self._cur, 0, np.arange(nw), nd)
+            self._log("mh_randn", out.copy())
+            return out
         # DEMove: ``random.randn(ns, 1)``  (de.py:56)
         n = int(np.prod(shape))
         assert self._phase == "proposal"

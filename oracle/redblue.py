@@ -13,6 +13,9 @@ Follows, line by line:
   with ``_get_nondiagonal_pairs`` (``de.py:67-77``) decoded analytically
    instead of materialising the O(Nc^2) table
 * ``DESnookerMove.get_proposal`` .............. ``src/emcee/moves/de_snooker.py:31-46``
+* ``WalkMove.get_proposal`` ................... ``src/emcee/moves/walk.py:27-37``
+* ``MHMove.propose`` + ``GaussianMove`` ....... ``src/emcee/moves/mh.py:35-65``,
+  ``src/emcee/moves/gaussian.py:72-119``
 * ``EnsembleSampler.compute_log_prob`` guards . ``src/emcee/ensemble.py:476-479,550-551``
 
 Random numbers come from the counter-addressed draw specification in
@@ -25,7 +28,7 @@ import numpy as np
 
 from . import philox as px
 
-__all__ = ["Stretch", "DE", "Snooker", "OracleSampler", "de_pair_decode"]
+__all__ = ["Stretch", "DE", "Snooker", "Walk", "Gaussian", "OracleSampler", "de_pair_decode"]
 
 
 class _RedBlue(object):
@@ -60,6 +63,38 @@ class Snooker(_RedBlue):
         super().__init__(**kw)
 
 
+class Walk(_RedBlue):
+    kind = "walk"
+
+    def __init__(self, s=None, **kw):
+        self.s = s
+        super().__init__(**kw)
+
+
+class Gaussian(object):
+    """``GaussianMove(cov, mode, factor)`` (``gaussian.py:32-69``): scalar, vector or matrix ``cov``."""
+
+    kind = "gaussian"
+
+    def __init__(self, cov, mode="vector", factor=None):
+        c = np.asarray(cov, dtype=np.float64)
+        if c.ndim == 0:
+            self.form, self.scale = "iso", float(np.sqrt(c))  # gaussian.py:58
+        elif c.ndim == 1:
+            self.form, self.scale = "diag", np.sqrt(c)  # gaussian.py:45
+        elif c.ndim == 2 and c.shape[0] == c.shape[1]:
+            self.form, self.scale = "full", c  # gaussian.py:50 (the matrix itself)
+            if mode != "vector":
+                raise ValueError("'{0}' is not a recognized mode.".format(mode))  # gaussian.py:111
+        else:
+            raise ValueError("Invalid proposal scale dimensions")
+        if factor is not None and factor < 1.0:
+            raise ValueError("'factor' must be >= 1.0")
+        self.mode, self.factor = mode, factor
+        self.index = 0  # gaussian.py:64, advanced by mode="sequential"
+        self.nsplits, self.randomize_split, self.live_dangerously = 1, False, True
+
+
 def de_pair_decode(m, n):
     """Row ``m`` of ``_get_nondiagonal_pairs(n)`` (``de.py:67-77``) without the
     table: the first ``T = n(n-1)/2`` rows are ``np.tril_indices(n, -1)`` in
@@ -87,7 +122,7 @@ class OracleSampler(object):
         self.log_prob_fn = log_prob
         if moves is None:
             moves = [(Stretch(), 1.0)]
-        elif isinstance(moves, _RedBlue):
+        elif isinstance(moves, (_RedBlue, Gaussian)):
             moves = [(moves, 1.0)]
         self.moves = [m for m, _ in moves]
         w = np.array([w for _, w in moves], dtype=np.float64)
@@ -185,8 +220,65 @@ class OracleSampler(object):
         self.taps = dict(z=zi[:, 0], z1=zi[:, 1], z2=zi[:, 2])
         return q, (self.ndim - 1.0) * metropolis  # de_snooker.py:46
 
+    def _walk(self, mv, s, sets_c, step, split):
+        comp = np.concatenate(sets_c)  # walk.py:28
+        Ns, Nc = len(s), len(comp)
+        s0 = Nc if mv.s is None else int(mv.s)  # walk.py:32
+        q = np.empty_like(s)
+        z = px.normals(self.seed, step, split, np.arange(Ns), self.ndim)
+        c = self.coords[comp]
+        shared = None
+        for i in range(Ns):
+            if s0 == Nc:  # the whole complement, in its own order: one covariance for the split
+                if shared is None:
+                    shared = px.chol_psd(np.atleast_2d(np.cov(c, rowvar=0)))  # walk.py:35
+                L = shared
+            else:
+                inds = px.subset_indices(self.seed, step, split, i, Nc, s0)  # walk.py:34
+                L = px.chol_psd(np.atleast_2d(np.cov(c[inds], rowvar=0)))  # walk.py:35
+            q[i] = s[i] + L @ z[i]  # walk.py:36 with multivariate_normal := mean + chol(cov) z
+        self.taps = dict(z=z)
+        return q, np.zeros(Ns, dtype=np.float64)  # walk.py:37
+
+    # -- mh.py:35-65 with gaussian.py:72-119 as the proposal ------------------
+    def _propose_mh(self, mv, step):
+        N, D = self.nwalkers, self.ndim
+        x0 = self.coords
+        f = 1.0
+        if mv.factor is not None:  # gaussian.py:88-91
+            w0, w1, _, _ = px.draw_words(self.seed, step, 0, px.TAG_MOVE, np.array([1]))
+            lf = np.log(mv.factor)
+            f = np.exp(-lf + (lf - (-lf)) * float(px.u53(w0, w1)[0]))
+        if mv.form == "full":
+            z = px.normals(self.seed, step, 0, np.array([0]), D)[0]
+            xnew = x0 + f * (np.zeros(D) + px.chol_psd(mv.scale) @ z)  # gaussian.py:116-118: one draw for all walkers
+        else:
+            xnew = x0 + f * mv.scale * px.normals(self.seed, step, 0, np.arange(N), D)  # gaussian.py:97
+        if mv.mode == "vector":
+            q = xnew
+        else:
+            if mv.mode == "random":  # gaussian.py:100
+                w0, w1, _, _ = px.draw_words(self.seed, step, 0, px.TAG_PROP_B, np.arange(N))
+                dim = px.bounded64(w0, w1, D)
+            else:  # sequential, gaussian.py:102-103
+                dim = np.full(N, mv.index % D, dtype=np.int64)
+                mv.index = (mv.index + 1) % D
+            q = np.array(x0)
+            q[np.arange(N), dim] = xnew[np.arange(N), dim]  # gaussian.py:106-107
+        new_lp = self.compute_log_prob(q)  # mh.py:54
+        u0, u1, _, _ = px.draw_words(self.seed, step, 0, px.TAG_ACCEPT, np.arange(N))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lnpdiff = new_lp - self.log_prob + np.zeros(N)  # mh.py:57
+            acc = np.log(px.u53(u0, u1)) < lnpdiff  # mh.py:58
+        self.taps = dict(q=q, new_lp=new_lp, u_accept=px.u53(u0, u1))
+        self.coords[acc] = q[acc]  # mh.py:62 -> move.py:33
+        self.log_prob[acc] = new_lp[acc]
+        return acc
+
     # -- red_blue.py:52-106 --------------------------------------------------
     def _propose(self, mv, step):
+        if mv.kind == "gaussian":
+            return self._propose_mh(mv, step)
         N, D = self.nwalkers, self.ndim
         if N < 2 * D and not mv.live_dangerously:  # red_blue.py:64-70
             raise RuntimeError(
@@ -196,7 +288,7 @@ class OracleSampler(object):
             )
         accepted = np.zeros(N, dtype=bool)
         inds = px.split_assignment(self.seed, step, N, mv.nsplits, mv.randomize_split)
-        get = {"stretch": self._stretch, "de": self._de, "snooker": self._snooker}[mv.kind]
+        get = {"stretch": self._stretch, "de": self._de, "snooker": self._snooker, "walk": self._walk}[mv.kind]
         for split in range(mv.nsplits):
             sets = [np.flatnonzero(inds == j) for j in range(mv.nsplits)]  # red_blue.py:85
             act = sets[split]

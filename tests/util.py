@@ -32,16 +32,24 @@ def oracle_target(g):
     raise ValueError(kind)
 
 
+GAUSS_MODES = ("vector", "random", "sequential")
+
+
 def oracle_moves(g):
     out = []
-    for kind, w, nsplits, rand, p0, p1 in g["moves"]:
+    for k, (kind, w, nsplits, rand, p0, p1) in enumerate(g["moves"]):
         kw = dict(nsplits=int(nsplits), randomize_split=bool(rand))
         if kind == 0:
             m = rb.Stretch(a=p0, **kw)
         elif kind == 1:
             m = rb.DE(sigma=p0, gamma0=None if np.isnan(p1) else p1, **kw)
-        else:
+        elif kind == 2:
             m = rb.Snooker(gammas=p0, **kw)
+        elif kind == 3:
+            m = rb.Walk(s=None if np.isnan(p0) else int(p0), **kw)
+        else:
+            cov = g["move%d_cov" % k]
+            m = rb.Gaussian(cov if cov.ndim else float(cov), GAUSS_MODES[int(p0)], None if np.isnan(p1) else float(p1))
         out.append((m, w))
     return out
 
