@@ -67,7 +67,8 @@ constexpr int MOM_MAXB = 18;  // 8 * 18 = 144 >= 136 pairs of D = 128: one pass
 
 __global__ void __launch_bounds__(32 * MOM_WARPS)
     moments_partial_kernel(const double* __restrict__ X, int64_t nrows, int D, const double* __restrict__ shift,
-                           double* __restrict__ partial, int CH, int RS) {
+                           double* __restrict__ partial, int CH, int RS, const int32_t* __restrict__ rowidx,
+                           int skip_start, int skip_count) {
   extern __shared__ double xs[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -99,7 +100,12 @@ __global__ void __launch_bounds__(32 * MOM_WARPS)
       const int r = idx / Dp, d = idx - r * Dp;
       const int64_t row = chunk * CH + r;
       double v = 0.0;
-      if (row < nrows && d < D) v = X[(size_t)row * D + d] - shift[d];
+      if (row < nrows && d < D) {
+        // optional indirection: row r of the set is walker rowidx[r < skip_start ? r : r + skip_count]
+        // (the complement of a split in the order of red_blue.py:85-87)
+        const int64_t src = rowidx ? (int64_t)rowidx[row < skip_start ? row : row + skip_count] : row;
+        v = X[(size_t)src * D + d] - shift[d];
+      }
       xs[r * RS + d] = v;
     }
     __syncthreads();
@@ -324,7 +330,7 @@ size_t moments_partial_bytes(int D, int sm_count) {
 
 // acc[D + D*D] += [sum(x - shift), (x - shift)^T (x - shift)] over the rows of X
 cudaError_t launch_moments(const double* X, int64_t nrows, int D, const double* shift, double* partial, double* acc,
-                           int sm_count, cudaStream_t st) {
+                           int sm_count, cudaStream_t st, const int32_t* rowidx, int skip_start, int skip_count) {
   if (D > 1024) return cudaErrorNotSupported;
   if (nrows <= 0) return cudaSuccess;
   const int nblk = (D + 7) / 8, Dp = 8 * nblk;
@@ -341,7 +347,8 @@ cudaError_t launch_moments(const double* X, int64_t nrows, int D, const double* 
   if (grid > nchunks) grid = (int)nchunks;
   const int npairs = nblk * (nblk + 1) / 2;
   const int passes = (npairs + MOM_WARPS * MOM_MAXB - 1) / (MOM_WARPS * MOM_MAXB);
-  moments_partial_kernel<<<dim3(grid, passes), 32 * MOM_WARPS, smem, st>>>(X, nrows, D, shift, partial, CH, RS);
+  moments_partial_kernel<<<dim3(grid, passes), 32 * MOM_WARPS, smem, st>>>(X, nrows, D, shift, partial, CH, RS, rowidx,
+                                                                           skip_start, skip_count);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const size_t n = (size_t)D + (size_t)D * D;

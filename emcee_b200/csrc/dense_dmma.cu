@@ -295,7 +295,6 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
       for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++k) {
         const int b = (int)(k & 1u);
         const bool has_next = tile + tstride < ntiles;
-        const bool first = tile == tile0;
         auto issue_next = [&]() -> bool {
           nxt = prep(tile + tstride);
           const unsigned kn = k + 1;
@@ -312,8 +311,9 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < KB; ++j) sreg[j] = __ldcg(reinterpret_cast<const double2*>(srow + 8 * j));
         const double lp_old = __ldcg(a.logp + cur.w);
-        // steady state: the next tile's partner rows are requested BEFORE this tile is processed
-        if (has_next && !first && !issue_next()) return;
+        // the next tile's partner rows are requested BEFORE this tile is processed (also for the first
+        // tile of a half-step: its draws run while this tile's partner rows are still in flight)
+        if (has_next && !issue_next()) return;
         // ---- partner rows of this tile have landed: form the proposal over them
         const double zz = __shfl_sync(0xffffffffu, cur.zz, g);
         double* myC = slot + (size_t)b * SL::buf_doubles + (size_t)g * RS + 2 * t;
@@ -337,8 +337,6 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(barReady + b);
-        // first tile of a half-step: the consumer is idle, so its proposal went first
-        if (has_next && first && !issue_next()) return;
         cur = nxt;
       }
     }

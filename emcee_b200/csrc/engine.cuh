@@ -70,7 +70,12 @@ struct HalfStepArgs {
   double* tap_u;          // [N]
   int64_t* tap_active;    // [N]
   long long* timeline;    // dense_dmma instrumentation: [SM][consumer][tile<=TL_TILES][TL_EVENTS] cycles, or null
+  const double* qbuf;     // MOVE_PRECOMPUTED: proposals [a_count, D] written by a proposal kernel (moves_extra.cu)
 };
+
+// internal move kind of half_step_generic_kernel: the proposal of active rank i is row i of HalfStepArgs::qbuf and
+// the Hastings factor is 0 (WalkMove walk.py:37, GaussianMove gaussian.py:104); order == nullptr: walker id = i
+constexpr int MOVE_PRECOMPUTED = 100;
 
 struct Engine;  // defined in capi.cu
 
@@ -109,14 +114,28 @@ cudaError_t launch_dense_dmma(const HalfStepArgs& a, const HalfDesc& d0, const H
                               unsigned long long* gbar, unsigned long long gbar_base, int sm_count, bool pdl,
                               int* grid_out, cudaStream_t st);
 
+// ---- proposal generators of WalkMove / GaussianMove (moves_extra.cu) ----------------------------
+// acc = [S1 | S2] moment sums about a shift over n rows -> cov (np.cov) -> thresholded lower Cholesky factor L
+cudaError_t launch_cov_chol(const double* acc, double n, int D, double* cov, double* L, cudaStream_t st);
+cudaError_t launch_walk_shared_propose(const HalfStepArgs& a, const double* L, double* qbuf, cudaStream_t st);
+bool walk_subset_supported(int D, int s0);
+cudaError_t launch_walk_subset_propose(const HalfStepArgs& a, int s0, double* qbuf, cudaStream_t st);
+cudaError_t launch_gaussian_shift(const double* L, int D, double f, uint64_t seed, uint64_t step, double* v,
+                                  cudaStream_t st);
+cudaError_t launch_gaussian_propose(const double* x0, int64_t row0, int64_t nrows, int D, int form, const double* scale,
+                                    double f, int mode, int seq_dim, uint64_t seed, uint64_t step, double* qbuf,
+                                    cudaStream_t st);
+
 // ---- chain analysis (analysis.cu) ------------------------------------------------------------
 // column means of X[nrows, D] (fixed summation order); status (nullable) gets the non-finite flags
 cudaError_t launch_colmean(const double* X, int64_t nrows, int D, double* mean, int* status, cudaStream_t st);
 // acc[D + D*D] += [sum(x - shift), (x - shift)^T (x - shift)] over the rows of X (DMMA; D <= 1024);
 // partial: scratch of moments_partial_bytes(D, sm_count)
 size_t moments_partial_bytes(int D, int sm_count);
+// rowidx (nullable): row r of the set is walker rowidx[r < skip_start ? r : r + skip_count]
 cudaError_t launch_moments(const double* X, int64_t nrows, int D, const double* shift, double* partial, double* acc,
-                           int sm_count, cudaStream_t st);
+                           int sm_count, cudaStream_t st, const int32_t* rowidx = nullptr, int skip_start = 0,
+                           int skip_count = 0);
 
 // walker-averaged normalised autocorrelation function (autocorr.py:21-46,101-107), slab by slab
 int acf_fft_length(size_t n_t);

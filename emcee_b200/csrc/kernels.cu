@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) half_step_generic_kernel(const HalfStepAr
 
   double* q = smem + (size_t)gid * NROWS * D;
   double* xc = q + (size_t)(NROWS - 1) * D;  // centred row (dense model only)
-  const int64_t w = a.order[a.a_start + i];
+  const int64_t w = a.order ? (int64_t)a.order[a.a_start + i] : i;  // no table: the active set is every walker (MHMove)
   const double* s_row = a.coords + (size_t)w * D;  // the active walker is always local
 
   const u32x4 A = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_PROP_A, (uint32_t)i);
@@ -162,6 +162,14 @@ __global__ void __launch_bounds__(256) half_step_generic_kernel(const HalfStepAr
       if (!isfinite(v)) flag_nonfinite(v, a.status);
     }
     tap_scalar = gamma;
+  } else if (MOVE == MOVE_PRECOMPUTED) {
+    // WalkMove / GaussianMove: the proposal was written by its own kernel (moves_extra.cu); factors = 0
+    const double* qrow = a.qbuf + (size_t)(i - i_lo) * D;
+    for (int e = g; e < D; e += G) {
+      const double v = qrow[e];
+      q[e] = v;
+      if (!isfinite(v)) flag_nonfinite(v, a.status);
+    }
   } else {  // EB_MOVE_SNOOKER
     const u32x4 B = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_PROP_B, (uint32_t)i);
     int64_t cw[3];
@@ -298,6 +306,8 @@ cudaError_t launch_half_step_generic(int move_kind, const HalfStepArgs& a, cudaS
       return launch_generic_m<EB_MOVE_DE>(a, st);
     case EB_MOVE_SNOOKER:
       return launch_generic_m<EB_MOVE_SNOOKER>(a, st);
+    case MOVE_PRECOMPUTED:
+      return launch_generic_m<MOVE_PRECOMPUTED>(a, st);
   }
   return cudaErrorInvalidValue;
 }

@@ -24,7 +24,9 @@ enum : uint32_t {
   TAG_SHUFFLE = 2,  // split-permutation round keys (red_blue.py:79-80)
   TAG_PROP_A = 3,   // proposal draw block A of active rank i
   TAG_PROP_B = 4,   // proposal draw block B of active rank i
-  TAG_ACCEPT = 5    // Metropolis uniform of active rank i (red_blue.py:100)
+  TAG_ACCEPT = 5,   // Metropolis uniform of active rank i (red_blue.py:100)
+  TAG_NORMAL = 6,   // bulk standard normals of row i: block k = normals 2k, 2k+1 (walk.py:36, gaussian.py:97)
+  TAG_SUBSET = 7    // round keys of the helper-subset permutation of active rank i (walk.py:34)
 };
 
 constexpr int FEISTEL_ROUNDS = 8;

@@ -201,8 +201,9 @@ def test_device_autocorr_function_small_and_odd_lengths(shape):
         assert np.all(np.isnan(got)) and np.all(np.isnan(want))  # 0 / 0, as numpy gives
         return
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-10)
-    if shape == (3000, 2, 2):
-        np.testing.assert_allclose(s._engine.autocorr_function(x[:, :1, :1])[:16, 0], _FIX["acf_head"], rtol=1e-9, atol=1e-12)
+    if shape == (3000, 2, 2):  # the reference's function_1d on the fixture's own series (seed 5)
+        x5 = _ar1_chain(5, 3000, 2, 2)
+        np.testing.assert_allclose(s._engine.autocorr_function(x5[:, :1, :1])[:16, 0], _FIX["acf_head"], rtol=1e-9, atol=1e-12)
 
 
 def test_sampler_get_autocorr_time_uses_the_device():
