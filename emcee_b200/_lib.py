@@ -35,7 +35,7 @@ EB_COMM_ALLGATHER = 0
 EB_COMM_P2P = 1
 
 MODEL_KINDS = {"gauss_iso": 0, "gauss_dense": 1, "rosenbrock": 2, "ring": 3}
-MOVE_KINDS = {"stretch": 0, "de": 1, "snooker": 2}
+MOVE_KINDS = {"stretch": 0, "de": 1, "snooker": 2, "walk": 3, "gaussian": 4}
 
 
 class EbMove(C.Structure):
@@ -47,6 +47,12 @@ class EbMove(C.Structure):
         ("weight", C.c_double),
         ("p0", C.c_double),
         ("p1", C.c_double),
+        # ABI 2: GaussianMove
+        ("mode", C.c_int32),
+        ("reserved", C.c_int32),
+        ("seq_index", C.c_int64),
+        ("cov", C.POINTER(C.c_double)),
+        ("ncov", C.c_uint64),
     ]
 
 
@@ -77,6 +83,7 @@ _SIGNATURES = {
     ),
     "eb_get_naccepted": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "eb_reset_counters": (C.c_int, [C.c_void_p]),
+    "eb_move_picks": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t]),
     "eb_moments": (C.c_int, [C.c_void_p, _dp, _dp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "eb_walkers_gram": (C.c_int, [C.c_void_p, _dp, C.c_size_t, _dp, C.POINTER(C.c_int)]),
     "eb_autocorr": (C.c_int, [C.c_void_p, _dp, C.c_size_t, C.c_size_t, C.c_size_t, _dp]),
@@ -308,7 +315,22 @@ class Engine(object):
             arr[k].weight = float(w)
             arr[k].p0 = float(d["p0"])
             arr[k].p1 = float(d["p1"])
+            if d.get("cov") is not None:  # GaussianMove: the array must outlive the call -> kept on `arr`
+                cov = np.ascontiguousarray(d["cov"], dtype=np.float64)
+                keep = getattr(arr, "_keep", [])
+                keep.append(cov)
+                arr._keep = keep
+                arr[k].cov = cov.ctypes.data_as(_dp)
+                arr[k].ncov = cov.size
+                arr[k].mode = int(d.get("mode", 0))
+                arr[k].seq_index = int(d.get("seq_index", 0))
         return arr
+
+    def move_picks(self, nmoves):
+        """How many steps of the last stepping call ran each schedule entry."""
+        out = np.zeros(int(nmoves), dtype=np.uint64)
+        self._check(lib().eb_move_picks(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), int(nmoves)))
+        return out
 
     def step(self, moves, nsteps, want_accepted=True):
         arr = self.pack_moves(moves)

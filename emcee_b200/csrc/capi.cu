@@ -94,6 +94,13 @@ struct eb_ctx {
   unsigned long long mom_count = 0;
   bool mom_have_shift = false;
 
+  // WalkMove / GaussianMove scratch (moves_extra.cu)
+  double* qbuf = nullptr;       // [N, D] proposals
+  double* walk_work = nullptr;  // [D shift | D + D*D moment sums | D*D cov | D*D L]
+  double* gauss_dev = nullptr;  // per schedule entry: scale / factor L of GaussianMove
+  size_t gauss_cap = 0;
+  std::vector<uint64_t> picks;  // per schedule entry: steps of the last call that ran it
+
   Comm comm;  // multi-GPU (comm.h)
 
   std::string err;
@@ -252,6 +259,9 @@ int eb_destroy(eb_ctx* c) {
     if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
   }
   cudaFree(c->flush_buf);
+  cudaFree(c->qbuf);
+  cudaFree(c->walk_work);
+  cudaFree(c->gauss_dev);
   cudaFree(c->mom_acc);
   cudaFree(c->mom_shift);
   cudaFree(c->mom_partial);
@@ -521,15 +531,83 @@ namespace {
 struct Schedule {
   std::vector<eb_move> moves;
   std::vector<double> cdf;
+  // GaussianMove: form (0 scalar, 1 diagonal, 2 full) and where its scale / Cholesky factor sits in gauss_dev
+  std::vector<int> gform;
+  std::vector<size_t> goff;
 };
+
+// thresholded lower Cholesky factor (the draw specification's multivariate_normal; oracle/philox.py chol_psd)
+void chol_psd_host(const double* A, int D, std::vector<double>& L) {
+  L.assign((size_t)D * D, 0.0);
+  double m = 0.0;
+  for (int j = 0; j < D; ++j) m = std::max(m, A[(size_t)j * D + j]);
+  const double tol = 1e-12 * m;
+  for (int j = 0; j < D; ++j) {
+    double d = A[(size_t)j * D + j];
+    for (int k = 0; k < j; ++k) d -= L[(size_t)j * D + k] * L[(size_t)j * D + k];
+    if (!(d > tol)) continue;
+    const double piv = sqrt(d);
+    L[(size_t)j * D + j] = piv;
+    for (int i = j + 1; i < D; ++i) {
+      double v = A[(size_t)i * D + j];
+      for (int k = 0; k < j; ++k) v -= L[(size_t)i * D + k] * L[(size_t)j * D + k];
+      L[(size_t)i * D + j] = v / piv;
+    }
+  }
+}
 
 int build_schedule(eb_ctx* c, const eb_move* moves, size_t nmoves, Schedule& s) {
   if (!moves || nmoves == 0) FAIL(c, EB_ERR_INVALID, "eb_step: empty move schedule");
   s.moves.assign(moves, moves + nmoves);
   double tot = 0.0;
-  for (const eb_move& m : s.moves) {
-    if (m.kind < EB_MOVE_STRETCH || m.kind > EB_MOVE_SNOOKER)
+  s.gform.assign(nmoves, 0);
+  s.goff.assign(nmoves, 0);
+  std::vector<double> ghost;  // host image of gauss_dev
+  for (size_t mi = 0; mi < nmoves; ++mi) {
+    eb_move& m = s.moves[mi];
+    if (m.kind < EB_MOVE_STRETCH || m.kind > EB_MOVE_GAUSSIAN)
       FAIL(c, EB_ERR_INVALID, "eb_step: unknown move kind %d", m.kind);
+    if ((m.kind == EB_MOVE_WALK || m.kind == EB_MOVE_GAUSSIAN) && c->comm.nranks > 1)
+      FAIL(c, EB_ERR_UNSUPPORTED, "eb_step: WalkMove / GaussianMove are not sharded across GPUs yet");
+    if ((m.kind == EB_MOVE_WALK || m.kind == EB_MOVE_GAUSSIAN) && c->debug)
+      FAIL(c, EB_ERR_UNSUPPORTED, "eb_step: debug taps do not cover WalkMove / GaussianMove");
+    if (m.kind == EB_MOVE_GAUSSIAN) {
+      const size_t D = (size_t)c->D;
+      if (!m.cov || (m.ncov != 1 && m.ncov != D && m.ncov != D * D) || (D == 1 && m.ncov != 1))
+        FAIL(c, EB_ERR_INVALID, "Invalid proposal scale dimensions");  // gaussian.py:53-54
+      if (m.mode < EB_GAUSS_VECTOR || m.mode > EB_GAUSS_SEQUENTIAL)
+        FAIL(c, EB_ERR_INVALID, "eb_step: unknown GaussianMove mode %d", m.mode);
+      if (!isnan(m.p1) && m.p1 < 1.0) FAIL(c, EB_ERR_INVALID, "'factor' must be >= 1.0");  // gaussian.py:69-70
+      if (!(m.weight >= 0.0) || !isfinite(m.weight)) FAIL(c, EB_ERR_INVALID, "eb_step: bad move weight");
+      s.goff[mi] = ghost.size();
+      if (m.ncov == D * D && D > 1) {
+        if (m.mode != EB_GAUSS_VECTOR)
+          FAIL(c, EB_ERR_INVALID, "a full proposal covariance only supports mode 'vector'");  // gaussian.py:110-111
+        s.gform[mi] = 2;
+        std::vector<double> L;
+        chol_psd_host(m.cov, c->D, L);
+        ghost.insert(ghost.end(), L.begin(), L.end());
+        ghost.resize(ghost.size() + D);  // the shared shift v[D] of a step lives behind its factor
+      } else {
+        s.gform[mi] = m.ncov == 1 ? 0 : 1;
+        for (size_t k = 0; k < m.ncov; ++k) {
+          if (!(m.cov[k] >= 0.0)) FAIL(c, EB_ERR_INVALID, "GaussianMove: variances must be >= 0");
+          ghost.push_back(sqrt(m.cov[k]));  // gaussian.py:45,58
+        }
+      }
+      m.nsplits = 1;  // the split table of such a step is never read
+      m.randomize_split = 0;
+      tot += m.weight;
+      continue;
+    }
+    if (m.kind == EB_MOVE_WALK && !isnan(m.p0)) {
+      const int64_t nc_min = c->N - (c->N + m.nsplits - 1) / std::max(m.nsplits, 1);
+      if (m.p0 != floor(m.p0) || m.p0 < 2 || (m.nsplits >= 2 && m.p0 > (double)nc_min))
+        FAIL(c, EB_ERR_INVALID, "eb_step: WalkMove needs 2 <= s <= size of the smallest complement (got %g)", m.p0);
+      if ((int64_t)m.p0 != nc_min && !walk_subset_supported(c->D, (int)m.p0))
+        FAIL(c, EB_ERR_UNSUPPORTED, "eb_step: WalkMove with a helper subset is limited to ndim <= 64 and s <= 4096");
+    }
+    if (m.kind == EB_MOVE_WALK && c->D > 1024) FAIL(c, EB_ERR_UNSUPPORTED, "eb_step: WalkMove is limited to ndim <= 1024");
     if (m.nsplits < 2 || m.nsplits > MAX_SPLITS || m.nsplits > c->N)
       FAIL(c, EB_ERR_UNSUPPORTED, "eb_step: nsplits must be in [2, min(%d, nwalkers)] (got %d)", MAX_SPLITS,
            m.nsplits);
@@ -542,6 +620,19 @@ int build_schedule(eb_ctx* c, const eb_move* moves, size_t nmoves, Schedule& s) 
     tot += m.weight;
   }
   if (!(tot > 0.0)) FAIL(c, EB_ERR_INVALID, "eb_step: move weights sum to zero");
+  if (!ghost.empty()) {
+    if (ghost.size() > c->gauss_cap) {
+      CK(c, cudaStreamSynchronize(c->st));
+      cudaFree(c->gauss_dev);
+      c->gauss_dev = nullptr;
+      c->gauss_cap = 0;
+      CK(c, cudaMalloc(&c->gauss_dev, ghost.size() * sizeof(double)));
+      c->gauss_cap = ghost.size();
+    }
+    CK(c, cudaMemcpyAsync(c->gauss_dev, ghost.data(), ghost.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaStreamSynchronize(c->st));  // ghost is a local
+  }
+  c->picks.assign(nmoves, 0);
   // ensemble.py:128-129 then RandomState.choice(p=...): cdf = cumsum(p); cdf /= cdf[-1]
   s.cdf.resize(nmoves);
   double run = 0.0;
@@ -656,6 +747,106 @@ int launch_step_generic(eb_ctx* c, const eb_move& mv, uint64_t step, const int32
     c->tap_count = a.a_count;
     if (comm_after_split(c->comm, c->st, c->status_dev, launches)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
   }
+  return EB_OK;
+}
+
+int ensure_move_scratch(eb_ctx* c) {
+  const size_t D = (size_t)c->D;
+  if (!c->qbuf) CK(c, cudaMalloc(&c->qbuf, (size_t)c->N * D * sizeof(double)));
+  if (!c->walk_work && D <= 1024) CK(c, cudaMalloc(&c->walk_work, (2 * D + 3 * D * D) * sizeof(double)));
+  if (!c->mom_partial && D <= 1024) CK(c, cudaMalloc(&c->mom_partial, moments_partial_bytes(c->D, c->sm_count)));
+  return EB_OK;
+}
+
+// WalkMove (walk.py:27-37): per split a proposal kernel writes q[a_count, D], then the fused
+// log-prob + accept + update kernel consumes it
+int launch_step_walk(eb_ctx* c, const eb_move& mv, uint64_t step, const int32_t* order, uint64_t& launches) {
+  const int P = mv.nsplits;
+  int rc = check_walker_count(c, mv);
+  if (rc) return rc;
+  rc = ensure_move_scratch(c);
+  if (rc) return rc;
+  int start[MAX_SPLITS + 1];
+  split_starts(c->N, P, start);
+  HalfStepArgs a;
+  fill_base_args(c, mv, a);
+  a.order = order;
+  a.step = step;
+  a.qbuf = c->qbuf;
+  c->chain_ok = false;
+  const size_t D = (size_t)c->D;
+  double* shift = c->walk_work;
+  double* acc = shift + D;
+  double* cov = acc + D + D * D;
+  double* L = cov + D * D;
+  for (int split = 0; split < P; ++split) {
+    a.split = split;
+    a.a_start = start[split];
+    a.a_count = start[split + 1] - start[split];
+    a.i_lo = 0;
+    a.i_hi = a.a_count;
+    a.range = nullptr;
+    const int64_t Nc = c->N - a.a_count;
+    const int64_t s0 = isnan(mv.p0) ? Nc : (int64_t)mv.p0;  // walk.py:32
+    if (s0 == Nc) {
+      // every walker of the split draws from the covariance of the WHOLE complement (walk.py:34-35 with a
+      // permutation of all Nc rows): computed once -- moment sums on the tensor pipe, then a D x D factorisation
+      CK(c, launch_colmean(c->coords, c->N, c->D, shift, nullptr, c->st));  // any shift will do: the ensemble mean
+      CK(c, cudaMemsetAsync(acc, 0, (D + D * D) * sizeof(double), c->st));
+      CK(c, launch_moments(c->coords, Nc, c->D, shift, c->mom_partial, acc, c->sm_count, c->st, order, a.a_start,
+                           a.a_count));
+      CK(c, launch_cov_chol(acc, (double)Nc, c->D, cov, L, c->st));
+      CK(c, launch_walk_shared_propose(a, L, c->qbuf, c->st));
+      launches += 5;
+    } else {
+      CK(c, launch_walk_subset_propose(a, (int)s0, c->qbuf, c->st));
+      ++launches;
+    }
+    CK(c, launch_half_step_generic(MOVE_PRECOMPUTED, a, c->st));
+    ++launches;
+  }
+  c->last_kernel = "walk";
+  return EB_OK;
+}
+
+// MHMove with the Gaussian proposal (mh.py:35-65, gaussian.py:72-119): every walker is proposed at once
+int launch_step_gaussian(eb_ctx* c, const Schedule& s, size_t mi, uint64_t step, uint64_t& launches) {
+  const eb_move& mv = s.moves[mi];
+  int rc = ensure_move_scratch(c);
+  if (rc) return rc;
+  const int D = c->D;
+  double f = 1.0;
+  if (!isnan(mv.p1)) {  // gaussian.py:88-91  exp(uniform(-log f, log f))
+    const u32x4 w = draw_words(c->seed, step, 0, TAG_MOVE, 1);
+    const double lf = log(mv.p1);
+    f = exp(-lf + (lf - (-lf)) * u53(w.x, w.y));
+  }
+  const int seq_dim = (int)(((uint64_t)mv.seq_index + c->picks[mi]) % (uint64_t)D);  // gaussian.py:102-103
+  const double* dev = c->gauss_dev + s.goff[mi];
+  const int form = s.gform[mi];
+  const double* scale = dev;
+  c->chain_ok = false;
+  if (form == 2) {
+    double* v = c->gauss_dev + s.goff[mi] + (size_t)D * D;
+    CK(c, launch_gaussian_shift(dev, D, f, c->seed, step, v, c->st));
+    scale = v;
+    ++launches;
+  }
+  CK(c, launch_gaussian_propose(c->coords, 0, c->N, D, form, scale, f, mv.mode, seq_dim, c->seed, step, c->qbuf, c->st));
+  HalfStepArgs a;
+  fill_base_args(c, mv, a);
+  a.order = nullptr;  // the active set is every walker, in walker order
+  a.step = step;
+  a.split = 0;
+  a.a_start = 0;
+  a.a_count = (int)c->N;
+  a.i_lo = 0;
+  a.i_hi = (int)c->N;
+  a.range = nullptr;
+  a.qbuf = c->qbuf;
+  CK(c, launch_half_step_generic(MOVE_PRECOMPUTED, a, c->st));
+  launches += 2;
+  c->last_kernel = "gaussian";
   return EB_OK;
 }
 
@@ -829,9 +1020,15 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
           rc = flush_dmma(c, *grp_move, grp, launches);
           if (rc) return rc;
         }
-        rc = launch_step_generic(c, mv, c->step, c->order + (off + k) * (size_t)c->N, off + k, launches);
+        if (mv.kind == EB_MOVE_WALK)
+          rc = launch_step_walk(c, mv, c->step, c->order + (off + k) * (size_t)c->N, launches);
+        else if (mv.kind == EB_MOVE_GAUSSIAN)
+          rc = launch_step_gaussian(c, s, pick[k], c->step, launches);
+        else
+          rc = launch_step_generic(c, mv, c->step, c->order + (off + k) * (size_t)c->N, off + k, launches);
         if (rc) return rc;
       }
+      c->picks[pick[k]] += 1;
       c->step += 1;
       if (c->moments_every > 0 && c->step % c->moments_every == 0) {
         rc = accumulate_moments(c, launches);
@@ -1006,6 +1203,12 @@ int eb_get_naccepted(eb_ctx* c, uint64_t* naccepted) {
   if (rc) return rc;
   CK(c, cudaMemcpyAsync(naccepted, c->nacc, (size_t)c->N * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->st));
   CK(c, cudaStreamSynchronize(c->st));
+  return EB_OK;
+}
+
+int eb_move_picks(const eb_ctx* c, uint64_t* picks, size_t nmoves) {
+  if (!c || !picks) return EB_ERR_INVALID;
+  for (size_t k = 0; k < nmoves; ++k) picks[k] = k < c->picks.size() ? c->picks[k] : 0;
   return EB_OK;
 }
 

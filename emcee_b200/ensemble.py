@@ -240,6 +240,16 @@ class EnsembleSampler(object):
     def _schedule(self):
         return [(m.descriptor(), w) for m, w in zip(self._moves, self._raw_weights)]
 
+    def _after_steps(self):
+        """Advance the host mirrors of stateful moves by what the engine just ran (``GaussianMove``
+        mode ``"sequential"`` keeps a running dimension index, ``gaussian.py:102-103``)."""
+        stateful = [m for m in self._moves if hasattr(m, "_advance")]
+        if stateful:
+            picks = self._engine.move_picks(len(self._moves))
+            for m, p in zip(self._moves, picks):
+                if hasattr(m, "_advance"):
+                    m._advance(int(p), self.ndim)
+
     def sample(
         self,
         initial_state,
@@ -333,10 +343,12 @@ class EnsembleSampler(object):
                     b = self.backend
                     k0, k1 = b.iteration, b.iteration + iterations
                     eng.step_store(sched, total, checkpoint_step, b.chain[k0:k1], b.log_prob[k0:k1], b.accepted)
+                    self._after_steps()
                     b.iteration = k1
                     b.random_state = self.random_state
                 else:
                     eng.step(sched, total, want_accepted=False)
+                    self._after_steps()
             refresh()
             if pbar is not None:
                 pbar.update(iterations)
@@ -349,16 +361,19 @@ class EnsembleSampler(object):
         counter = iter(int, 1) if iterations is None else range(iterations)
         for _ in counter:
             # the steps of this yield window; at most the last one is stored
+            sched = self._schedule()  # stateful moves (GaussianMove "sequential") change between calls
             last_is_checkpoint = store and (i + yield_step) % checkpoint_step == 0
             if last_is_checkpoint and native_store:
                 b = self.backend
                 k = b.iteration
                 eng.step_store(sched, yield_step, yield_step, b.chain[k : k + 1], b.log_prob[k : k + 1], b.accepted)
+                self._after_steps()
                 b.iteration = k + 1
                 b.random_state = self.random_state
                 refresh()
             else:
                 accepted = eng.step(sched, yield_step, want_accepted=last_is_checkpoint)
+                self._after_steps()
                 refresh()
                 if last_is_checkpoint:
                     self.backend.save_step(state, accepted)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EB_ABI_VERSION 1
+#define EB_ABI_VERSION 2
 
 typedef enum eb_status {
   EB_OK = 0,
@@ -56,8 +56,16 @@ typedef enum eb_model_kind {
 typedef enum eb_move_kind {
   EB_MOVE_STRETCH = 0, /* p0 = a        (stretch.py:22)                         */
   EB_MOVE_DE = 1,      /* p0 = sigma, p1 = gamma0 or NaN for 2.38/sqrt(2 ndim) (de.py:28,33-38) */
-  EB_MOVE_SNOOKER = 2  /* p0 = gammas   (de_snooker.py:26); nsplits must be 4 (:28) */
+  EB_MOVE_SNOOKER = 2, /* p0 = gammas   (de_snooker.py:26); nsplits must be 4 (:28) */
+  EB_MOVE_WALK = 3,    /* p0 = s, the number of helper walkers, or NaN for the whole complement (walk.py:24,32) */
+  EB_MOVE_GAUSSIAN = 4 /* MHMove with a Gaussian proposal (mh.py:35-65, gaussian.py:32-119): `mode`, p1 = factor
+                          or NaN, `cov`/`ncov` = the cov argument (1 scalar, ndim vector, ndim*ndim matrix);
+                          not a red-blue move: nsplits / randomize_split are ignored */
 } eb_move_kind;
+
+typedef enum eb_gaussian_mode { /* gaussian.py:63,99-104 */
+  EB_GAUSS_VECTOR = 0, EB_GAUSS_RANDOM = 1, EB_GAUSS_SEQUENTIAL = 2
+} eb_gaussian_mode;
 
 /* one entry of the move schedule (ensemble.py:115-129) with the RedBlueMove
  * constructor arguments (moves/red_blue.py:37-42) */
@@ -69,6 +77,12 @@ typedef struct eb_move {
   double weight;            /* un-normalised; normalised as ensemble.py:128-129 */
   double p0;
   double p1;
+  /* ABI 2: GaussianMove only (zero / NULL otherwise) */
+  int32_t mode;             /* eb_gaussian_mode */
+  int32_t reserved;
+  int64_t seq_index;        /* mode "sequential": the proposal's `index` (gaussian.py:64) when the call starts */
+  const double* cov;        /* host pointer, read during the call */
+  uint64_t ncov;
 } eb_move;
 
 typedef struct eb_ctx eb_ctx;
@@ -146,6 +160,10 @@ int eb_step_store(eb_ctx* ctx, const eb_move* moves, size_t nmoves, uint64_t nst
 /* per-walker number of accepted proposals since creation / eb_reset_counters
  * (numerator of acceptance_fraction, ensemble.py:555-558). */
 int eb_get_naccepted(eb_ctx* ctx, uint64_t* naccepted);
+/* how many steps of the LAST eb_step / eb_step_store call ran each entry of its move schedule
+ * (picks[nmoves]): the host mirror of a stateful move (GaussianMove mode "sequential",
+ * gaussian.py:102-103) advances its index by this count. */
+int eb_move_picks(const eb_ctx* ctx, uint64_t* picks, size_t nmoves);
 int eb_reset_counters(eb_ctx* ctx);
 
 /* ---- chain analysis on the device --------------------------------------- */

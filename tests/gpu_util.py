@@ -21,16 +21,25 @@ def device_model(kind, g=None, target=None):
     raise ValueError(kind)
 
 
-def device_moves(rows):
+GAUSS_MODES = ("vector", "random", "sequential")
+
+
+def device_moves(rows, g=None):
     out = []
-    for kind, w, nsplits, rand, p0, p1 in rows:
+    for k, (kind, w, nsplits, rand, p0, p1) in enumerate(rows):
         kw = dict(randomize_split=bool(rand))
         if kind == 0:
             m = moves.StretchMove(a=p0, nsplits=int(nsplits), **kw)
         elif kind == 1:
             m = moves.DEMove(sigma=p0, gamma0=None if np.isnan(p1) else p1, nsplits=int(nsplits), **kw)
-        else:
+        elif kind == 2:
             m = moves.DESnookerMove(gammas=p0, **kw)
+        elif kind == 3:
+            m = moves.WalkMove(s=None if np.isnan(p0) else int(p0), nsplits=int(nsplits), **kw)
+        else:
+            cov = g["move%d_cov" % k]
+            m = moves.GaussianMove(cov if cov.ndim else float(cov), mode=GAUSS_MODES[int(p0)],
+                                   factor=None if np.isnan(p1) else float(p1))
         out.append((m, w))
     return out
 
@@ -38,7 +47,7 @@ def device_moves(rows):
 def golden_sampler(g):
     return emcee_b200.EnsembleSampler(
         int(g["nwalkers"]), int(g["ndim"]), device_model(str(g["model_kind"]), g=g),
-        moves=device_moves(g["moves"]), seed=int(g["seed"]),
+        moves=device_moves(g["moves"], g), seed=int(g["seed"]),
     )
 
 

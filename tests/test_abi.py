@@ -30,11 +30,13 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_abi_version():
-    assert _lib.lib().eb_abi_version() == 1
+    assert _lib.lib().eb_abi_version() == 2
 
 
 def test_eb_move_layout_matches_header():
-    assert ctypes.sizeof(_lib.EbMove) == 4 * 4 + 3 * 8
+    # ABI 2: kind, nsplits, randomize_split, live_dangerously | weight, p0, p1 | mode, reserved | seq_index | cov* | ncov
+    assert ctypes.sizeof(_lib.EbMove) == 4 * 4 + 3 * 8 + 2 * 4 + 8 + 8 + 8
+    assert _lib.EbMove.cov.offset == 56 and _lib.EbMove.ncov.offset == 64
 
 
 @pytest.mark.skipif(_lib.device_count() > 0, reason="only meaningful without a GPU")
@@ -69,6 +71,33 @@ def test_state_protocol():
     assert np.all(x == 0)
     again = emcee_b200.State(s4)
     assert again.coords is s4.coords and again.blobs is s4.blobs
+
+
+def test_new_move_constructors_validate_like_the_reference():
+    # reference: moves/gaussian.py:36-79, moves/mh.py:31-33, moves/walk.py:24-26
+    from emcee_b200 import moves
+
+    g = moves.GaussianMove(0.5)
+    d = g.descriptor()
+    assert d["kind"] == "gaussian" and d["mode"] == 0 and d["cov"].shape == (1,) and np.isnan(d["p1"])
+    assert moves.GaussianMove([0.1, 0.2], mode="random", factor=2.0).descriptor()["p1"] == 2.0
+    assert moves.GaussianMove(np.eye(3)).ndim == 3
+    with pytest.raises(ValueError, match="not a recognized mode"):
+        moves.GaussianMove(np.eye(3), mode="random")
+    with pytest.raises(ValueError, match="not a recognized mode"):
+        moves.GaussianMove(1.0, mode="bogus")
+    with pytest.raises(ValueError, match="factor"):
+        moves.GaussianMove(1.0, factor=0.5)
+    with pytest.raises(ValueError, match="Invalid proposal scale dimensions"):
+        moves.GaussianMove(np.zeros((2, 3)))
+    with pytest.raises(NotImplementedError):
+        moves.MHMove(lambda x, rng: (x, np.zeros(len(x))))
+    seq = moves.GaussianMove(np.ones(4), mode="sequential")
+    seq._advance(6, 4)
+    assert seq.index == 2 and seq.descriptor()["seq_index"] == 2
+    w = moves.WalkMove(s=7, nsplits=3)
+    assert w.descriptor()["kind"] == "walk" and w.descriptor()["p0"] == 7.0 and w.descriptor()["nsplits"] == 3
+    assert np.isnan(moves.WalkMove().descriptor()["p0"])
 
 
 def test_move_update_host():

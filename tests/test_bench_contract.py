@@ -21,6 +21,11 @@ def test_reference_arm_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
         assert key in d, key
     assert d["impl"] == "reference" and d["dtype"] == "f64" and d["vs_baseline"] is None and d["steps"] == 3
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference (baseline/_ref, packaged by baseline/make_ref.py) when it travelled, else the port
+    have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "emcee_reference.zip"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["port"] > 0
+    if have_ref:
+        assert d["cpu_baseline"]["reference_vectorize"] > 0 and d["cpu_baseline"]["reference_pool"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] > 0
     assert "workload" in d["config"]

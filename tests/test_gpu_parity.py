@@ -36,6 +36,10 @@ def _tols(g):
         return True, 0.0, 0.0
     if 2 in kinds:
         return False, 1e-5, 1e-6
+    if kinds & {3, 4}:
+        # WalkMove / GaussianMove: normals through device log / sincos (last-ulp differences from numpy's),
+        # WalkMove also through a Cholesky factor whose rounding scales with cond(cov)
+        return False, 1e-9, 1e-11
     return False, 1e-12, 1e-12
 
 
@@ -65,10 +69,15 @@ def test_golden_single_steps(name):
     tolerance is tight for every move (and exact for the stretch move)."""
     g = load_golden(name)
     s = golden_sampler(g)
-    eng, sched = s._engine, s._schedule()
+    eng = s._engine
     exact = _tols(g)[0]
+    step_tol = 1e-11 if set(g["moves"][:, 0].astype(int)) & {3, 4} else 1e-12
     prev_c, prev_lp = g["p0"], g["lp0"]
     for k in range(g["chain"].shape[0]):
+        for m in s._moves:  # GaussianMove "sequential" (single-move schedules here): k earlier picks
+            if hasattr(m, "index"):
+                m.index = k % int(g["ndim"])
+        sched = s._schedule()
         eng.set_state(prev_c, prev_lp)
         eng.set_rng(int(g["seed"]), k)
         acc = eng.step(sched, 1)
@@ -77,7 +86,7 @@ def test_golden_single_steps(name):
         if exact:
             assert np.array_equal(coords, g["chain"][k]), (name, k)
         else:
-            np.testing.assert_allclose(coords, g["chain"][k], rtol=1e-12, atol=1e-12, err_msg="%s step %d" % (name, k))
+            np.testing.assert_allclose(coords, g["chain"][k], rtol=step_tol, atol=step_tol, err_msg="%s step %d" % (name, k))
         np.testing.assert_allclose(lp, g["log_prob"][k], rtol=LP_RTOL, atol=LP_ATOL)
         prev_c, prev_lp = g["chain"][k], g["log_prob"][k]
 
