@@ -79,7 +79,7 @@ struct eb_ctx {
   bool fused_last = false;  // the last dense_dmma launch carried the P2P barrier itself
   int dmma_stagger = 1;
   int dmma_group = 1;  // half-steps per persistent dense_dmma launch (1: a launch per half-step)
-  bool pdl = true;       // dense_dmma launches chain as programmatic dependents (prologue overlaps the previous tail)
+  int pdl = 1;           // dense_dmma launches chain as programmatic dependents (1: one GPU only, 2: sharded too)
   bool chain_ok = false; // the last operation enqueued on the stream is a dense_dmma kernel of this run
   // multi-GPU: log_prob / accept mask / counters (and, P2P, coords) of rows owned by OTHER ranks are stale
   // on this rank until the next collective read (eb_get_state, eb_get_naccepted, ...) replicates them
@@ -868,7 +868,9 @@ int flush_dmma(eb_ctx* c, const eb_move& mv, DmmaGroup& grp, uint64_t& launches)
   // P2P: the peer barrier rides inside the kernel (wait at its start, between its half-steps, signal at its end)
   const bool fused = comm_fuse_barrier(c->comm, a, grp.nhalf);
   c->fused_last = fused;
-  const bool pdl = c->pdl && c->chain_ok && grp.nhalf == 1;
+  // (sharded ensembles: measured slower with the dependent launch -- the early CTAs only add pollers on the
+  // peer flags -- so it is opt-in there: option "pdl" = 2)
+  const bool pdl = c->chain_ok && grp.nhalf == 1 && (c->comm.nranks > 1 ? c->pdl >= 2 : c->pdl >= 1);
   int grid = 0;
   CK(c, launch_dense_dmma(a, c->descs_host[grp.first], c->descs_dev + grp.first, grp.nhalf, bound, c->gbar, c->gbar_count, c->sm_count, pdl,
                           &grid, c->st));
@@ -1411,7 +1413,7 @@ int eb_set_option(eb_ctx* c, const char* name, int64_t value) {
     return EB_OK;
   }
   if (!strcmp(name, "pdl")) {
-    c->pdl = value != 0;
+    c->pdl = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
     return EB_OK;
   }
   if (!strcmp(name, "moments_every")) {

@@ -49,12 +49,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 __host__ __device__ constexpr int packed_blocks(int KB) { return KB * (KB + 1); }  // 2 * KB(KB+1)/2
-// landing buffers of one pair: two buffers of [8 rows][D + 8] doubles (partner rows, then the
-// proposal); the +8 (64 B) row skew makes the 16-byte fragment accesses of 8 consecutive lanes hit
-// 32 distinct banks
+// landing slot of one pair: [s|c][8 rows][D + 8] doubles; the +8 (64 B) row skew
+// makes the 16-byte fragment accesses of 8 consecutive lanes hit 32 distinct banks
 __host__ __device__ constexpr int row_stride(int KB) { return 8 * KB + 8; }
 
-// what the producer hands to the consumer besides q (one record per landing buffer)
+// what the producer hands to the consumer besides q (one record per tile, two in flight)
 struct TileMeta {
   double factor[8];  // (ndim - 1) log zz                              (stretch.py:31)
   double log_u[8];   // log of the accept uniform                      (red_blue.py:100)
@@ -66,14 +65,13 @@ template <int KB>
 struct SmemLayout {
   static constexpr size_t L_doubles = (size_t)packed_blocks(KB) * 32;
   static constexpr size_t mu_doubles = 8 * KB;
-  static constexpr size_t buf_doubles = 8 * row_stride(KB);       // one landing buffer
-  static constexpr size_t slot_doubles = 2 * buf_doubles;         // the two buffers of a pair
+  static constexpr size_t slot_doubles = 2 * 8 * row_stride(KB);
   static constexpr size_t off_mu = L_doubles;
   static constexpr size_t off_slots = off_mu + mu_doubles;
   static constexpr size_t off_meta = off_slots + DMMA_CONSUMERS * slot_doubles;  // in doubles
   static constexpr size_t meta_bytes = sizeof(TileMeta) * 2 * DMMA_CONSUMERS;
   static constexpr size_t off_bars_bytes = off_meta * sizeof(double) + meta_bytes;
-  static constexpr int nbars = 1 + 6 * DMMA_CONSUMERS;
+  static constexpr int nbars = 1 + 3 * DMMA_CONSUMERS;
   static constexpr size_t off_abort_bytes = off_bars_bytes + nbars * sizeof(uint64_t);
   static constexpr size_t total_bytes = off_abort_bytes + 16;
 };
@@ -157,15 +155,6 @@ __device__ __forceinline__ bool peer_wait(const unsigned* my_flags, int rank, in
   return __all_sync(0xffffffffu, ok);
 }
 
-// Pipeline of one producer/consumer pair (v8).  Two landing buffers B0, B1; tile k of the pair uses
-// buffer k & 1, its `use` index is k >> 1 (mbarrier phase parity = use & 1):
-//   producer: [wait barFree[b] of use-1]  TMA partner rows of tile k -> B[b]   (barFull[b])
-//             wait barFull[b]; own rows by 16-byte loads; q = c - (c - s) z over the partner rows;
-//             meta[b]; arrive barReady[b]
-//   consumer: wait barReady[b]; q -> registers; arrive barFree[b]; DMMA block; accept; store
-// The partner rows of tile k+1 are requested before tile k is turned into a proposal, so they have
-// two tile times to arrive (they may come from a peer GPU over NVLink); the own rows are local
-// and are only prefetched into L2.
 template <int KB, bool HAS_MEAN>
 __global__ void __launch_bounds__(DMMA_THREADS, 1)
     half_step_dense_dmma_kernel(const HalfStepArgs a, const HalfDesc d0, const HalfDesc* __restrict__ descs,
@@ -179,20 +168,27 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   double* sSlots = sL + SL::off_slots;
   TileMeta* sMeta = reinterpret_cast<TileMeta*>(sL + SL::off_meta);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + SL::off_bars_bytes);
+  // CTA-wide abort flag: a producer that gives up on a lost peer / CTA sets it, every wait polls it, so all
+  // warps leave and the host reports FLAG_COMM_TIMEOUT instead of the kernel spinning into a trap
   volatile int* sAbort = reinterpret_cast<volatile int*>(smem_raw + SL::off_abort_bytes);
+  uint64_t* barL = bars;                                  // packed factor landed
+  uint64_t* barFull = bars + 1;                           // [pair] TMA: rows of a tile landed
+  uint64_t* barReady = bars + 1 + DMMA_CONSUMERS;         // [pair] producer: proposal written
+  uint64_t* barFree = bars + 1 + 2 * DMMA_CONSUMERS;      // [pair] consumer: slot may be refilled
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_producer = warp >= DMMA_CONSUMERS;
   const int pair = is_producer ? warp - DMMA_CONSUMERS : warp;
   const int g = lane >> 2, t = lane & 3;
-  uint64_t* barL = bars;                                       // packed factor landed
-  uint64_t* barFull = bars + 1 + 2 * pair;                     // [b] TMA: partner rows of a tile landed
-  uint64_t* barReady = bars + 1 + 2 * DMMA_CONSUMERS + 2 * pair;  // [b] producer: proposal written
-  uint64_t* barFree = bars + 1 + 4 * DMMA_CONSUMERS + 2 * pair;   // [b] consumer: buffer may be refilled
 
   if (tid == 0) {
     *sAbort = 0;
-    for (int c = 0; c < SL::nbars; ++c) mbar_init(bars + c, 1);
+    mbar_init(barL, 1);
+    for (int c = 0; c < DMMA_CONSUMERS; ++c) {
+      mbar_init(barFull + c, 1);
+      mbar_init(barReady + c, 1);
+      mbar_init(barFree + c, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (HAS_MEAN)
@@ -207,18 +203,20 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   const int64_t tstride = (int64_t)gridDim.x * DMMA_CONSUMERS;
   const int64_t tile0 = (int64_t)blockIdx.x + (int64_t)gridDim.x * pair;  // SM-major deal
   double* slot = sSlots + (size_t)pair * SL::slot_doubles;
+  double* myS = slot + (size_t)g * RS + 2 * t;  // this lane's 16-byte chunks of row g
+  double* myC = myS + 8 * RS;                   // partner row, later the proposal
   TileMeta* meta = sMeta + 2 * pair;
   const bool multi = a.p2p_peer_flags != nullptr;
-  unsigned k = 0;  // tiles this pair has handled so far in the launch (buffer = k & 1, use = k >> 1)
+  unsigned k = 0;  // tiles this pair has handled so far in the launch (mbarrier phase counter)
 
   if (is_producer) {
-    // ================= producer: draws, lookups, TMA partner gather, proposal =================
+    // ================= producer: draws, lookups, TMA row gather, proposal =================
     const double dm1 = (double)a.D - 1.0;
     const int row = lane & 7;
     // per-row quantities of one tile (every lane mirrors row lane & 7)
     struct Prep {
       int32_t w, wp;
-      double zz, factor, log_u;
+      double zz, factor, log_u, lp_old;
       bool valid;
     };
     for (int h = 0; h < nhalf; ++h) {
@@ -228,8 +226,8 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
       const int i_lo = rg.x, i_hi = rg.y;
       const int64_t ntiles = ((int64_t)i_hi - i_lo + 7) >> 3;
       const int64_t Nc = a.N - d.a_count;
-      // draws + index lookups: independent of the walker state, so they run ahead of every barrier
-      auto prep = [&](int64_t tile) -> Prep {
+      // draws + index lookups: independent of the walker state, so they run ahead of the grid barrier
+      auto prep = [&](int64_t tile, bool with_lp) -> Prep {
         Prep p;
         int64_t i = (int64_t)i_lo + tile * 8 + row;
         p.valid = i < i_hi;
@@ -243,35 +241,58 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
         const u32x4 U = draw_words(a.seed, d.step, (uint32_t)d.split, TAG_ACCEPT, (uint32_t)i);
         p.log_u = log(u53(U.x, U.y));
         p.factor = __dmul_rn(dm1, log(p.zz));  // stretch.py:31
-        // own row (always local): pull its lines into L2 now, it is read with plain loads later
-        const char* own = reinterpret_cast<const char*>(a.coords + (size_t)p.w * D);
-        for (int l = lane >> 3; l * 128 < D * 8; l += 4) prefetch_l2(own + l * 128);
+        p.lp_old = with_lp ? a.logp[p.w] : 0.0;
         return p;
       };
-      // the 8 partner-row copies of one tile into landing buffer b (possibly from a peer GPU over NVLink)
-      auto issue = [&](const Prep& p, int b) {
-        if (lane == 0) mbar_arrive_expect_tx(barFull + b, 8u * D * (unsigned)sizeof(double));
+      // publish the meta record and launch the 16 row copies of one tile into the landing slot
+      auto issue = [&](Prep& p, int par, bool load_lp) {
+        if (lane == 0) mbar_arrive_expect_tx(barFull + pair, 16u * D * (unsigned)sizeof(double));
         __syncwarp();
+        if (lane < 16) {
+          const bool partner = lane >= 8;
+          const int64_t wr = partner ? (int64_t)p.wp : (int64_t)p.w;
+          const double* base =
+              (partner && a.peer_coords != nullptr) ? a.peer_coords[wr / a.rows_per_rank] : a.coords;
+          bulk_g2s(slot + (size_t)(partner ? 8 : 0) * RS + (size_t)row * RS, base + (size_t)wr * D,
+                   (unsigned)(D * sizeof(double)), barFull + pair);
+        }
+        if (load_lp) p.lp_old = a.logp[p.w];  // behind the row copies: off the post-barrier critical path
+        TileMeta* m = meta + par;
         if (lane < 8) {
-          const int64_t wr = (int64_t)p.wp;
-          const double* base = (a.peer_coords != nullptr) ? a.peer_coords[wr / a.rows_per_rank] : a.coords;
-          bulk_g2s(slot + (size_t)b * SL::buf_doubles + (size_t)row * RS, base + (size_t)wr * D,
-                   (unsigned)(D * sizeof(double)), barFull + b);
+          m->factor[row] = p.factor;
+          m->log_u[row] = p.log_u;
+          m->lp_old[row] = p.lp_old;
+          m->w[row] = p.valid ? p.w : -1;
         }
       };
-      const bool have = tile0 < ntiles;
       Prep cur{}, nxt{};
-      if (have) cur = prep(tile0);
-
-      // ---- the state written by the previous half-step may be read from here on ----
+      if (tile0 < ntiles) cur = prep(tile0, false);  // (the old log-prob is state: it is read behind the barrier)
       if (h == 0) {
-        pdl_wait();  // previous kernel of the stream (programmatic launch) has completed and flushed
+        // everything above (barrier set-up, factor copy, first draws and index lookups) overlapped the tail of
+        // the previous kernel when this one was launched as its programmatic dependent; the state that
+        // kernel wrote may be read from here on
+        pdl_wait();
         pdl_launch_dependents();
+        // multi-GPU: no peer may still be reading (or not yet have written) what this half-step touches
         if (multi && !peer_wait(a.p2p_my_flags, a.p2p_rank, a.p2p_nranks, a.p2p_wait, lane, a.status)) {
           *sAbort = 1;
           return;
         }
+        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of the previous kernel / peers -> our TMA reads
+        // launch start: get the first rows moving before anything else.  All 8 pairs asking at once is a
+        // 19 MB burst (148 SMs x 8 slots x 16 KB) during which nobody computes -- and, sharded, a burst on
+        // the NVLink ports; with the stagger the second pair of each sub-partition asks only when the first
+        // pair's rows are in, so one consumer per sub-partition starts after half the burst.
+        if (tile0 < ntiles) {
+          // (best effort: a bounded peek at the neighbour's barrier, never a dependency)
+          if (a.dmma_stagger && pair >= DMMA_CONSUMERS / 2)
+            mbar_wait_for(barFull + pair - DMMA_CONSUMERS / 2, 0, multi ? 40000 : 12000);
+          issue(cur, (int)(k & 1u), true);
+        }
+        if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, true);
       } else {
+        if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, false);
+        // every CTA (of every rank) has finished writing half-step h-1: the state may be read again
         bool ok = true;
         if (lane == 0) ok = grid_wait(gbar, gbar_base + (unsigned long long)h * gridDim.x, a.status);
         ok = __shfl_sync(0xffffffffu, ok, 0);
@@ -280,47 +301,20 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
           *sAbort = 1;
           return;
         }
-      }
-      asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other SMs / GPUs -> our TMA reads
-      if (have) {
-        const int b = (int)(k & 1u);
-        if (k >= 2 && !mbar_wait_abortable(barFree + b, ((k >> 1) - 1) & 1u, sAbort)) return;
-        // launch start: all 8 pairs asking at once is a burst during which nobody computes; with the
-        // stagger the second pair of each sub-partition asks only when the first pair's rows are in
-        // (best effort, single GPU only: a bounded peek at the neighbour's barrier, never a dependency)
-        if (h == 0 && a.dmma_stagger && !multi && pair >= DMMA_CONSUMERS / 2)
-          mbar_wait_for(barFull - 2 * (DMMA_CONSUMERS / 2), 0, 12000);
-        issue(cur, b);
+        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other SMs / GPUs -> our TMA reads
+        if (tile0 < ntiles) {
+          // the slot was released by the consumer at the end of the previous half-step's last tile
+          if (k > 0 && !mbar_wait_abortable(barFree + pair, (k - 1) & 1u, sAbort)) return;
+          issue(cur, (int)(k & 1u), true);
+        }
       }
       for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++k) {
-        const int b = (int)(k & 1u);
-        const bool has_next = tile + tstride < ntiles;
-        auto issue_next = [&]() -> bool {
-          nxt = prep(tile + tstride);
-          const unsigned kn = k + 1;
-          if (kn >= 2 && !mbar_wait_abortable(barFree + (b ^ 1), ((kn >> 1) - 1) & 1u, sAbort)) return false;
-          issue(nxt, b ^ 1);
-          return true;
-        };
-        // own rows of this tile (always local): plain 16-byte loads issued NOW and consumed after the
-        // partner rows have landed -- their latency hides behind the next tile's draws and the wait for
-        // a free landing buffer instead of sitting on the producer's critical path
-        const int32_t wg = __shfl_sync(0xffffffffu, cur.w, g);
-        const double* srow = a.coords + (size_t)wg * D + 2 * t;
-        double2 sreg[KB];
-#pragma unroll
-        for (int j = 0; j < KB; ++j) sreg[j] = __ldcg(reinterpret_cast<const double2*>(srow + 8 * j));
-        const double lp_old = __ldcg(a.logp + cur.w);
-        // the next tile's partner rows are requested BEFORE this tile is processed (also for the first
-        // tile of a half-step: its draws run while this tile's partner rows are still in flight)
-        if (has_next && !issue_next()) return;
-        // ---- partner rows of this tile have landed: form the proposal over them
+        // ---- rows of this tile have landed: form the proposal over the partner rows
         const double zz = __shfl_sync(0xffffffffu, cur.zz, g);
-        double* myC = slot + (size_t)b * SL::buf_doubles + (size_t)g * RS + 2 * t;
-        if (!mbar_wait_abortable(barFull + b, (k >> 1) & 1u, sAbort)) return;
+        if (!mbar_wait_abortable(barFull + pair, k & 1u, sAbort)) return;
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
-          const double2 s2 = sreg[j];
+          const double2 s2 = *reinterpret_cast<const double2*>(myS + 8 * j);
           const double2 c2 = *reinterpret_cast<const double2*>(myC + 8 * j);
           // stretch.py:33  q = c - (c - s) * zz, each op rounded once (no FMA contraction)
           double2 q2;
@@ -328,16 +322,15 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
           q2.y = __dsub_rn(c2.y, __dmul_rn(__dsub_rn(c2.y, s2.y), zz));
           *reinterpret_cast<double2*>(myC + 8 * j) = q2;
         }
-        TileMeta* m = meta + b;
-        if (lane < 8) {
-          m->factor[row] = cur.factor;
-          m->log_u[row] = cur.log_u;
-          m->lp_old[row] = lp_old;
-          m->w[row] = cur.valid ? cur.w : -1;
-        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(barReady + b);
-        cur = nxt;
+        if (lane == 0) mbar_arrive(barReady + pair);
+        // ---- as soon as the consumer has the proposal in registers, refill the slot
+        if (tile + tstride < ntiles) {
+          cur = nxt;
+          if (!mbar_wait_abortable(barFree + pair, k & 1u, sAbort)) return;
+          issue(cur, (int)((k + 1) & 1u), h > 0 && tile == tile0);
+          if (tile + 2 * tstride < ntiles) nxt = prep(tile + 2 * tstride, true);
+        }
       }
     }
     return;
@@ -350,8 +343,8 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   long long* tl = a.timeline ? a.timeline + ((size_t)blockIdx.x * DMMA_CONSUMERS + pair) * TL_TILES * TL_EVENTS : nullptr;
   pdl_wait();  // nothing of this warp's global traffic may overtake the previous kernel
   pdl_launch_dependents();
-  // On an abort (a producer gave up on a lost peer) a consumer stops working but keeps walking the
-  // same sequence of named barriers as its siblings, so nobody is left waiting for a warp that left.
+  // On an abort a consumer stops working but keeps walking the same sequence of named barriers as its
+  // siblings, so nobody is left waiting for a warp that left.
   bool alive = mbar_wait_abortable(barL, 0, sAbort);
   for (int h = 0; h < nhalf; ++h) {
     const HalfDesc d = (h == 0) ? d0 : descs[h];
@@ -359,15 +352,13 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
     const int64_t ntiles = ((int64_t)rg.y - rg.x + 7) >> 3;
     unsigned kk = 0;
     for (int64_t tile = tile0; alive && tile < ntiles; tile += tstride, ++k, ++kk) {
-      const int b = (int)(k & 1u);
-      const TileMeta* m = meta + b;
-      const double* myC = slot + (size_t)b * SL::buf_doubles + (size_t)g * RS + 2 * t;
+      const TileMeta* m = meta + (k & 1u);
       long long* tlk = (tl && h == nhalf - 1 && kk < TL_TILES && lane == 0) ? tl + kk * TL_EVENTS : nullptr;
       if (tlk) {
         tlk[0] = (long long)tile;
         tlk[1] = clock64() - t_entry;
       }
-      if (!mbar_wait_abortable(barReady + b, (k >> 1) & 1u, sAbort)) {
+      if (!mbar_wait_abortable(barReady + pair, k & 1u, sAbort)) {
         alive = false;
         break;
       }
@@ -382,7 +373,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
       const int32_t w = m->w[g];
       const double factor = m->factor[g], log_u = m->log_u[g], lp_old = m->lp_old[g];
       __syncwarp();
-      if (lane == 0) mbar_arrive(barFree + b);  // buffer and meta may be refilled while this tile computes
+      if (lane == 0) mbar_arrive(barFree + pair);  // slot and meta may be refilled while this tile computes
       if (tlk) tlk[3] = clock64() - t_entry;
 
       // ---- y = L^T (q - mu) block by block on the tensor pipe; rs = sum_n y_n^2
