@@ -392,10 +392,10 @@ class Engine(object):
 
     def debug_timeline(self):
         """[SM, consumer, tile, event] cycle stamps of the last dense_dmma half-step."""
-        buf = np.zeros(1 << 20, dtype=np.int64)
+        buf = np.zeros(1 << 21, dtype=np.int64)
         n = C.c_size_t()
         self._check(lib().eb_debug_timeline(self._h, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(n)))
-        return buf[: n.value].reshape(-1, 8, 8, 6)
+        return buf[: n.value].reshape(-1, 8, 8, 10)  # events 0..5 consumer, 6..8 producer (dense_dmma.cu)
 
     # -- multi-GPU ---------------------------------------------------------------
     @staticmethod

@@ -80,6 +80,7 @@ struct eb_ctx {
   int dmma_stagger = 1;
   int dmma_group = 1;  // half-steps per persistent dense_dmma launch (1: a launch per half-step)
   int pdl = 1;           // dense_dmma launches chain as programmatic dependents (1: one GPU only, 2: sharded too)
+  bool local_first = true;  // sharded dense_dmma: tiles with local partners first, peer barrier deferred behind them
   bool chain_ok = false; // the last operation enqueued on the stream is a dense_dmma kernel of this run
   // multi-GPU: log_prob / accept mask / counters (and, P2P, coords) of rows owned by OTHER ranks are stale
   // on this rank until the next collective read (eb_get_state, eb_get_naccepted, ...) replicates them
@@ -863,6 +864,7 @@ int flush_dmma(eb_ctx* c, const eb_move& mv, DmmaGroup& grp, uint64_t& launches)
   fill_base_args(c, mv, a);
   a.order = c->order;  // chunk base; HalfDesc::order_step selects the table
   a.range = c->comm.nranks > 1 ? c->comm.ranges : nullptr;
+  a.aperm = (c->comm.nranks > 1 && c->local_first) ? c->comm.aperm : nullptr;
   int bound = grp.max_count;
   if (c->comm.nranks > 1 && c->comm.rows_per_rank < bound) bound = (int)c->comm.rows_per_rank;
   // P2P: the peer barrier rides inside the kernel (wait at its start, between its half-steps, signal at its end)
@@ -983,6 +985,11 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
                                     cm.rows_per_rank * cm.rank, cm.rows_per_rank * (cm.rank + 1),
                                     cm.nranks > 1 ? cm.ranges : nullptr, c->st));
           ++launches;
+          if (cm.nranks > 1 && cm.aperm) {
+            CK(c, launch_locality_tables(c->order, c->info_dev, cm.ranges, (int)build, c->N, c->seed, c->step,
+                                         cm.rows_per_rank, cm.rank, cm.aperm, c->st));
+            ++launches;
+          }
           c->chain_ok = false;
         }
       }
@@ -1410,6 +1417,10 @@ int eb_set_option(eb_ctx* c, const char* name, int64_t value) {
   if (!strcmp(name, "dmma_group")) {
     if (value < 1) FAIL(c, EB_ERR_INVALID, "dmma_group must be >= 1");
     c->dmma_group = (int)std::min<int64_t>(value, 1 << 20);
+    return EB_OK;
+  }
+  if (!strcmp(name, "dmma_local_first")) {
+    c->local_first = value != 0;
     return EB_OK;
   }
   if (!strcmp(name, "pdl")) {

@@ -201,6 +201,7 @@ int comm_init(Comm& c, const char* id128, int rank, int nranks, int mode, int64_
   NCK(c, api.CommInitRank(&comm, nranks, id, rank));
   c.nccl = comm;
   CCK(c, cudaMalloc(&c.ranges, table_cap * MAX_SPLITS * sizeof(int2)));
+  if (mode == EB_COMM_P2P) CCK(c, cudaMalloc(&c.aperm, table_cap * (size_t)N * sizeof(int32_t)));
   CCK(c, cudaMalloc(&c.done, sizeof(unsigned)));
   CCK(c, cudaMemsetAsync(c.done, 0, sizeof(unsigned), st));
   CCK(c, cudaMemsetAsync(c.flags, 0, MAX_RANKS * sizeof(unsigned), st));
@@ -300,6 +301,7 @@ void comm_destroy(Comm& c) {
   cudaFree(c.peer_coords_dev);
   cudaFree(c.peer_flags_dev);
   cudaFree(c.ranges);
+  cudaFree(c.aperm);
   cudaFree(c.done);
   if (c.nccl) nccl_api().CommDestroy(static_cast<ncclComm_t>(c.nccl));
   c = Comm();

@@ -26,6 +26,7 @@ struct Comm {
   double* coords = nullptr;   // this rank's [N, D] buffer (+ barrier flags in its tail)
   unsigned* flags = nullptr;  // this rank's barrier flags [MAX_RANKS], inside the coords allocation
   int2* ranges = nullptr;     // [table_cap, MAX_SPLITS] active-rank range of this rank per (step, set)
+  int32_t* aperm = nullptr;   // [table_cap, N] P2P: owned active ranks per (step, set), partner-local first
   void* nccl = nullptr;       // ncclComm_t
   // P2P
   void* peer_base[MAX_RANKS] = {nullptr};

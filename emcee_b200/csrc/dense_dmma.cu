@@ -171,6 +171,10 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   // CTA-wide abort flag: a producer that gives up on a lost peer / CTA sets it, every wait polls it, so all
   // warps leave and the host reports FLAG_COMM_TIMEOUT instead of the kernel spinning into a trap
   volatile int* sAbort = reinterpret_cast<volatile int*>(smem_raw + SL::off_abort_bytes);
+  // multi-GPU: number of half-steps of this launch whose peer barrier this CTA has passed (written by the
+  // producer of pair 0).  Tiles whose partners are all local start before it; remote fetches and every
+  // store of an accepted row wait for it.
+  volatile int* sPeers = sAbort + 1;
   uint64_t* barL = bars;                                  // packed factor landed
   uint64_t* barFull = bars + 1;                           // [pair] TMA: rows of a tile landed
   uint64_t* barReady = bars + 1 + DMMA_CONSUMERS;         // [pair] producer: proposal written
@@ -183,6 +187,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
 
   if (tid == 0) {
     *sAbort = 0;
+    *sPeers = 0;
     mbar_init(barL, 1);
     for (int c = 0; c < DMMA_CONSUMERS; ++c) {
       mbar_init(barFull + c, 1);
@@ -211,13 +216,18 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
 
   if (is_producer) {
     // ================= producer: draws, lookups, TMA row gather, proposal =================
+    // optional stamps of the LAST half-step, events 6..8 of the tile's record (cycles since this warp entered
+    // the kernel): 6 rows requested, 7 rows landed, 8 proposal published
+    const long long t_entry_p = clock64();
+    long long* tlp = (a.timeline && lane == 0)
+                         ? a.timeline + ((size_t)blockIdx.x * DMMA_CONSUMERS + pair) * TL_TILES * TL_EVENTS : nullptr;
     const double dm1 = (double)a.D - 1.0;
     const int row = lane & 7;
     // per-row quantities of one tile (every lane mirrors row lane & 7)
     struct Prep {
       int32_t w, wp;
       double zz, factor, log_u, lp_old;
-      bool valid;
+      bool valid, remote;
     };
     for (int h = 0; h < nhalf; ++h) {
       const HalfDesc d = (h == 0) ? d0 : descs[h];  // the first one travels in the launch parameters
@@ -227,11 +237,13 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
       const int64_t ntiles = ((int64_t)i_hi - i_lo + 7) >> 3;
       const int64_t Nc = a.N - d.a_count;
       // draws + index lookups: independent of the walker state, so they run ahead of the grid barrier
+      const int32_t* aperm = a.aperm ? a.aperm + (size_t)d.order_step * a.N + d.a_start : nullptr;
       auto prep = [&](int64_t tile, bool with_lp) -> Prep {
         Prep p;
         int64_t i = (int64_t)i_lo + tile * 8 + row;
         p.valid = i < i_hi;
         if (!p.valid) i = (int64_t)i_hi - 1;
+        if (aperm) i = __ldg(aperm + i);  // sharded: tiles are built partner-local first (locality_table_kernel)
         const u32x4 A = draw_words(a.seed, d.step, (uint32_t)d.split, TAG_PROP_A, (uint32_t)i);
         const double tt = __dadd_rn(__dmul_rn(__dsub_rn(a.p0, 1.0), u53(A.x, A.y)), 1.0);  // stretch.py:30
         p.zz = __ddiv_rn(__dmul_rn(tt, tt), a.p0);
@@ -242,10 +254,32 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
         p.log_u = log(u53(U.x, U.y));
         p.factor = __dmul_rn(dm1, log(p.zz));  // stretch.py:31
         p.lp_old = with_lp ? a.logp[p.w] : 0.0;
+        p.remote = multi && (p.wp / a.rows_per_rank != a.p2p_rank);
         return p;
       };
+      // multi-GPU: the peer barrier of this half-step (every rank has finished the previous one).  Pair 0's
+      // producer waits on the peer flags and publishes the result to the CTA; the others wait for that.
+      auto peers_ready = [&]() -> bool {
+        if (!multi || *sPeers > h) return true;
+        if (pair == 0) {
+          if (!peer_wait(a.p2p_my_flags, a.p2p_rank, a.p2p_nranks, a.p2p_wait + (unsigned)h, lane, a.status)) {
+            *sAbort = 1;
+            return false;
+          }
+          __syncwarp();
+          if (lane == 0) *sPeers = h + 1;
+        } else {
+          while (*sPeers <= h) {
+            if (*sAbort) return false;
+            __nanosleep(64);
+          }
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");  // peers' generic-proxy writes -> our TMA reads
+        return true;
+      };
       // publish the meta record and launch the 16 row copies of one tile into the landing slot
-      auto issue = [&](Prep& p, int par, bool load_lp) {
+      auto issue = [&](Prep& p, int par, bool load_lp) -> bool {
+        if (__any_sync(0xffffffffu, p.remote) && !peers_ready()) return false;
         if (lane == 0) mbar_arrive_expect_tx(barFull + pair, 16u * D * (unsigned)sizeof(double));
         __syncwarp();
         if (lane < 16) {
@@ -264,6 +298,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
           m->lp_old[row] = p.lp_old;
           m->w[row] = p.valid ? p.w : -1;
         }
+        return true;
       };
       Prep cur{}, nxt{};
       if (tile0 < ntiles) cur = prep(tile0, false);  // (the old log-prob is state: it is read behind the barrier)
@@ -273,12 +308,11 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
         // kernel wrote may be read from here on
         pdl_wait();
         pdl_launch_dependents();
-        // multi-GPU: no peer may still be reading (or not yet have written) what this half-step touches
-        if (multi && !peer_wait(a.p2p_my_flags, a.p2p_rank, a.p2p_nranks, a.p2p_wait, lane, a.status)) {
-          *sAbort = 1;
-          return;
-        }
-        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of the previous kernel / peers -> our TMA reads
+        // (a completed predecessor kernel needs no proxy fence: griddepcontrol.wait returns with its writes
+        // performed; the fence costs ~1 us per launch).  Sharded: the peer barrier is NOT taken here -- tiles
+        // whose partners are local start at once; issue() takes it before the first remote fetch, pair 0's
+        // producer right after its first tile at the latest, the consumers before their first store.
+        if (multi && !a.aperm && !peers_ready()) return;  // natural tile order: barrier first, as before
         // launch start: get the first rows moving before anything else.  All 8 pairs asking at once is a
         // 19 MB burst (148 SMs x 8 slots x 16 KB) during which nobody computes -- and, sharded, a burst on
         // the NVLink ports; with the stagger the second pair of each sub-partition asks only when the first
@@ -287,8 +321,12 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
           // (best effort: a bounded peek at the neighbour's barrier, never a dependency)
           if (a.dmma_stagger && pair >= DMMA_CONSUMERS / 2)
             mbar_wait_for(barFull + pair - DMMA_CONSUMERS / 2, 0, multi ? 40000 : 12000);
-          issue(cur, (int)(k & 1u), true);
+          if (tlp) tlp[6] = clock64() - t_entry_p;
+          if (!issue(cur, (int)(k & 1u), true)) return;
         }
+        // pair 0 takes the barrier now if its first tile did not need it (the flags normally arrive while that
+        // tile's rows are in flight); the other producers only wait for it inside issue(), when they need it
+        if (pair == 0 && !peers_ready()) return;
         if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, true);
       } else {
         if (tile0 + tstride < ntiles) nxt = prep(tile0 + tstride, false);
@@ -296,22 +334,26 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
         bool ok = true;
         if (lane == 0) ok = grid_wait(gbar, gbar_base + (unsigned long long)h * gridDim.x, a.status);
         ok = __shfl_sync(0xffffffffu, ok, 0);
-        if (ok && multi) ok = peer_wait(a.p2p_my_flags, a.p2p_rank, a.p2p_nranks, a.p2p_wait + (unsigned)h, lane, a.status);
         if (!ok) {
           *sAbort = 1;
           return;
         }
-        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other SMs / GPUs -> our TMA reads
+        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other SMs -> our TMA reads
+        if (multi && !a.aperm && !peers_ready()) return;
         if (tile0 < ntiles) {
           // the slot was released by the consumer at the end of the previous half-step's last tile
           if (k > 0 && !mbar_wait_abortable(barFree + pair, (k - 1) & 1u, sAbort)) return;
-          issue(cur, (int)(k & 1u), true);
+          if (!issue(cur, (int)(k & 1u), true)) return;
         }
+        if (pair == 0 && !peers_ready()) return;
       }
       for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++k) {
         // ---- rows of this tile have landed: form the proposal over the partner rows
         const double zz = __shfl_sync(0xffffffffu, cur.zz, g);
         if (!mbar_wait_abortable(barFull + pair, k & 1u, sAbort)) return;
+        long long* tlq = (tlp && h == nhalf - 1 && (tile - tile0) / tstride < TL_TILES && lane == 0)
+                             ? tlp + ((tile - tile0) / tstride) * TL_EVENTS : nullptr;
+        if (tlq) tlq[7] = clock64() - t_entry_p;
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
           const double2 s2 = *reinterpret_cast<const double2*>(myS + 8 * j);
@@ -324,11 +366,14 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(barReady + pair);
+        if (tlq) tlq[8] = clock64() - t_entry_p;
         // ---- as soon as the consumer has the proposal in registers, refill the slot
         if (tile + tstride < ntiles) {
           cur = nxt;
           if (!mbar_wait_abortable(barFree + pair, k & 1u, sAbort)) return;
-          issue(cur, (int)((k + 1) & 1u), h > 0 && tile == tile0);
+          if (tlq && (tile - tile0) / tstride + 1 < TL_TILES)
+            tlq[TL_EVENTS + 6] = clock64() - t_entry_p;  // (stamp 6 of the NEXT tile: its rows are requested)
+          if (!issue(cur, (int)((k + 1) & 1u), h > 0 && tile == tile0)) return;
           if (tile + 2 * tstride < ntiles) nxt = prep(tile + 2 * tstride, true);
         }
       }
@@ -351,6 +396,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
     const int2 rg = a.range ? a.range[(size_t)d.order_step * MAX_SPLITS + d.split] : make_int2(0, d.a_count);
     const int64_t ntiles = ((int64_t)rg.y - rg.x + 7) >> 3;
     unsigned kk = 0;
+    bool peers_passed = false;
     for (int64_t tile = tile0; alive && tile < ntiles; tile += tstride, ++k, ++kk) {
       const TileMeta* m = meta + (k & 1u);
       long long* tlk = (tl && h == nhalf - 1 && kk < TL_TILES && lane == 0) ? tl + kk * TL_EVENTS : nullptr;
@@ -431,6 +477,19 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
       // ---- Metropolis accept + in-place update (red_blue.py:96-104, move.py:29-34)
       const double lnpdiff = __dsub_rn(__dadd_rn(factor, lp_new), lp_old);
       const bool acc = (w >= 0) && (lnpdiff > log_u);
+      if (multi && !peers_passed) {
+        // sharded: a slower peer may still be reading this rank's rows for ITS previous half-step; nothing is
+        // overwritten before every peer has published that it is through (normally true long before now)
+        while (*sPeers <= h) {
+          if (*sAbort) break;
+          __nanosleep(64);
+        }
+        peers_passed = !*sAbort;
+        if (!peers_passed) {
+          alive = false;
+          break;
+        }
+      }
       if (acc) {
         double* dst = a.coords + (size_t)w * D + 2 * t;
 #pragma unroll

@@ -13,7 +13,7 @@ namespace eb {
 
 constexpr int MAX_SPLITS = 32;      // split_table_kernel uses one warp per set
 constexpr int TABLE_THREADS = 1024;
-constexpr int TL_TILES = 8, TL_EVENTS = 6;  // dense_dmma timeline buffer shape
+constexpr int TL_TILES = 8, TL_EVENTS = 10;  // dense_dmma timeline buffer shape (6 consumer + 4 producer stamps)
 
 // device status flags (OR-ed by kernels, read back after every call)
 enum : int {
@@ -60,6 +60,9 @@ struct HalfStepArgs {
   int a_start, a_count;  // active set = order[a_start .. a_start + a_count)
   int i_lo, i_hi;        // active ranks processed by this GPU (an upper bound for grid sizing when `range` is set)
   const int2* range;     // multi-GPU: device-resident [i_lo, i_hi) of this rank for this (step, split), or null
+  // multi-GPU (P2P, dense_dmma): per (step, split) the owned active ranks with LOCAL partners first -- tile t
+  // takes active ranks aperm[a_start + i_lo + 8 t ..]; null: natural order.  Same layout as `order`.
+  const int32_t* aperm;
   int c_start[3], c_count[3];  // snooker: the three complement sets (ascending j != split)
   uint64_t seed, step;
   double p0, p1;  // stretch: a | de: g0, sigma | snooker: gammas
@@ -84,6 +87,12 @@ struct Engine;  // defined in capi.cu
 cudaError_t launch_split_tables(int32_t* order, const StepInfo* info_dev, int nsteps_chunk, int64_t N,
                                 uint64_t seed, uint64_t step0, int64_t w_lo, int64_t w_hi, int2* ranges,
                                 cudaStream_t st);
+// multi-GPU: for every (step, split) of the chunk, the active ranks [i_lo, i_hi) this rank owns, those whose
+// stretch partner lives on this rank first (stable) -- tiles built from the front need no NVLink traffic and no
+// peer barrier, so a half-step starts computing while the barrier and the first remote rows are still in flight
+cudaError_t launch_locality_tables(const int32_t* order, const StepInfo* info_dev, const int2* ranges, int nsteps_chunk,
+                                   int64_t N, uint64_t seed, uint64_t step0, int64_t rows_per_rank, int rank,
+                                   int32_t* aperm, cudaStream_t st);
 cudaError_t launch_half_step_generic(int move_kind, const HalfStepArgs& a, cudaStream_t st);
 // TMA row-gather variant for the HBM-bound models (tma_rows.cu); *used == false: not applicable, use the generic one
 cudaError_t launch_half_step_tma(int move_kind, const HalfStepArgs& a, int sm_count, cudaStream_t st, bool* used);

@@ -98,6 +98,86 @@ cudaError_t launch_split_tables(int32_t* order, const StepInfo* info_dev, int ns
 }
 
 // ===========================================================================
+// locality tables (multi-GPU): owned active ranks, partner-local first
+// ===========================================================================
+// One block per (step of the chunk, split).  The stretch partner of active rank i is a pure function of
+// (seed, step, split, i) and of the split table (stretch.py:32, DESIGN.md draw specification), so the order
+// can be tabulated ahead for a whole chunk of steps like the split tables themselves.
+__global__ void __launch_bounds__(TABLE_THREADS) locality_table_kernel(const int32_t* __restrict__ order_base,
+                                                                       const StepInfo* __restrict__ info,
+                                                                       const int2* __restrict__ ranges, int64_t N,
+                                                                       uint64_t seed, uint64_t step0,
+                                                                       int64_t rows_per_rank, int rank,
+                                                                       int32_t* __restrict__ aperm_base) {
+  __shared__ int warp_cnt[2][32];
+  __shared__ int base_sh[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int P = info[blockIdx.x].nsplits, split = blockIdx.y;
+  if (split >= P) return;
+  const uint64_t step = step0 + blockIdx.x;
+  const int32_t* order = order_base + (size_t)blockIdx.x * (size_t)N;
+  int32_t* aperm = aperm_base + (size_t)blockIdx.x * (size_t)N;
+  int a_start = 0;
+  for (int j = 0; j < split; ++j) a_start += (int)((N - j + P - 1) / P);
+  const int a_count = (int)((N - split + P - 1) / P);
+  const int2 rg = ranges[(size_t)blockIdx.x * MAX_SPLITS + split];
+  const int i_lo = rg.x, i_hi = rg.y;
+  const int64_t Nc = N - a_count;
+  auto is_local = [&](int i) -> bool {
+    const u32x4 A = draw_words(seed, step, (uint32_t)split, TAG_PROP_A, (uint32_t)i);
+    const int64_t r = (int64_t)bounded64(A.z, A.w, (uint64_t)Nc);  // stretch.py:32
+    const int64_t wp = order[r < a_start ? r : r + a_count];
+    return wp / rows_per_rank == rank;
+  };
+  // pass 1: how many owned active ranks have a local partner
+  int mine = 0;
+  for (int i = i_lo + tid; i < i_hi; i += TABLE_THREADS) mine += is_local(i) ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (lane == 0) warp_cnt[0][warp] = mine;
+  __syncthreads();
+  if (tid == 0) {
+    int tot = 0;
+    for (int k = 0; k < TABLE_THREADS / 32; ++k) tot += warp_cnt[0][k];
+    base_sh[0] = 0;    // next slot of the local group
+    base_sh[1] = tot;  // next slot of the remote group
+  }
+  __syncthreads();
+  // pass 2: stable two-way partition, chunk by chunk
+  for (int c0 = i_lo; c0 < i_hi; c0 += TABLE_THREADS) {
+    const int i = c0 + tid;
+    const bool valid = i < i_hi;
+    const bool loc = valid && is_local(i);
+    const unsigned bl = __ballot_sync(0xffffffffu, loc);
+    const unsigned br = __ballot_sync(0xffffffffu, valid && !loc);
+    if (lane == 0) {
+      warp_cnt[0][warp] = __popc(bl);
+      warp_cnt[1][warp] = __popc(br);
+    }
+    __syncthreads();
+    int off = 0;
+    const int grp = loc ? 0 : 1;
+    for (int k = 0; k < warp; ++k) off += warp_cnt[grp][k];
+    const unsigned b = loc ? bl : br;
+    if (valid) aperm[a_start + base_sh[grp] + off + __popc(b & ((1u << lane) - 1u)) + i_lo] = i;
+    __syncthreads();
+    if (tid < 2) {
+      int tot = 0;
+      for (int k = 0; k < TABLE_THREADS / 32; ++k) tot += warp_cnt[tid][k];
+      base_sh[tid] += tot;
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_locality_tables(const int32_t* order, const StepInfo* info_dev, const int2* ranges, int nsteps_chunk,
+                                   int64_t N, uint64_t seed, uint64_t step0, int64_t rows_per_rank, int rank,
+                                   int32_t* aperm, cudaStream_t st) {
+  locality_table_kernel<<<dim3(nsteps_chunk, MAX_SPLITS), TABLE_THREADS, 0, st>>>(order, info_dev, ranges, N, seed, step0,
+                                                                                 rows_per_rank, rank, aperm);
+  return cudaGetLastError();
+}
+
+// ===========================================================================
 // generic fused half-step: proposal + log-prob + accept + update
 // ===========================================================================
 // G lanes per active walker; the proposal row is staged in shared memory

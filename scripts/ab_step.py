@@ -19,6 +19,7 @@ ap.add_argument("--flush", type=int, default=0)
 ap.add_argument("--group", type=int, default=0)
 ap.add_argument("--pdl", type=int, default=-1)
 ap.add_argument("--nwalkers", type=int, default=65536)
+ap.add_argument("--local-first", type=int, default=-1)
 ap.add_argument("--tag", default="")
 a = ap.parse_args()
 rdv = dist.Rendezvous()
@@ -32,6 +33,8 @@ if a.group > 0:
     eng.set_option("dmma_group", a.group)
 if a.pdl >= 0:
     eng.set_option("pdl", a.pdl)
+if a.local_first >= 0:
+    eng.set_option("dmma_local_first", a.local_first)
 sched = [(dict(kind="stretch", nsplits=2, randomize_split=True, live_dangerously=False, p0=2.0, p1=float("nan")), 1.0)]
 eng.set_state(w["p0"])
 eng.step(sched, 20, want_accepted=False)

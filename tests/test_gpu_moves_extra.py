@@ -81,7 +81,7 @@ def test_mixture_with_sequential_index_across_calls():
     for st in s.sample(st, iterations=6, store=False, skip_initial_state_check=True):
         o.run(1)
         np.testing.assert_allclose(st.coords, o.coords, rtol=1e-9, atol=1e-10)
-    st = s.run_mcmc(None, 5, skip_initial_state_check=True)
+    st = s.run_mcmc(st, 5, skip_initial_state_check=True)
     o.run(5)
     np.testing.assert_allclose(st.coords, o.coords, rtol=1e-9, atol=1e-10)
     assert dm[0][0].index == om[0][0].index
