@@ -907,7 +907,10 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
   if (comm_begin(c->comm, c->st, c->status_dev, launches)) FAIL(c, EB_ERR_COMM, "%s", c->comm.err.c_str());
   c->fused_last = false;
   const bool multi = c->comm.nranks > 1;
-  // ranks that exchange whole row blocks through NCCL do so after every split: one half-step per launch
+  // sharded ensembles run one half-step per launch: NCCL exchanges whole row blocks after every split, and the
+  // P2P peer barrier rides on the kernel boundary (a persistent launch with the peer barrier between its
+  // half-steps measured no faster -- profiles/r02_ab_2gpu.md -- and was dropped)
+  const bool one_per_launch = multi;
   const bool exchange_each = multi && c->comm.mode == EB_COMM_ALLGATHER;
   std::vector<size_t> pick;
   uint64_t done = 0;
@@ -986,8 +989,9 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
                                     cm.nranks > 1 ? cm.ranges : nullptr, c->st));
           ++launches;
           if (cm.nranks > 1 && cm.aperm) {
+            // front group = one tile (8 walkers) for each of the 8 consumer warps of every SM: the first round
             CK(c, launch_locality_tables(c->order, c->info_dev, cm.ranges, (int)build, c->N, c->seed, c->step,
-                                         cm.rows_per_rank, cm.rank, cm.aperm, c->st));
+                                         cm.rows_per_rank, cm.rank, 64 * c->sm_count, cm.aperm, c->st));
             ++launches;
           }
           c->chain_ok = false;
@@ -1008,7 +1012,7 @@ int run_steps(eb_ctx* c, const Schedule& s, uint64_t nsteps, uint64_t sync_every
           grp.nhalf += 1;
           grp.max_count = std::max(grp.max_count, (int)d.a_count);
           ++desc_cursor;
-          if (exchange_each || (grp.nhalf >= c->dmma_group && split + 1 < mv.nsplits)) {
+          if (one_per_launch || (grp.nhalf >= c->dmma_group && split + 1 < mv.nsplits)) {
             rc = flush_dmma(c, mv, grp, launches);
             if (rc) return rc;
             if (exchange_each) {

@@ -339,13 +339,12 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
           return;
         }
         asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other SMs -> our TMA reads
-        if (multi && !a.aperm && !peers_ready()) return;
+        // (persistent launches are single-GPU: the host runs sharded ensembles one half-step per launch)
         if (tile0 < ntiles) {
           // the slot was released by the consumer at the end of the previous half-step's last tile
           if (k > 0 && !mbar_wait_abortable(barFree + pair, (k - 1) & 1u, sAbort)) return;
           if (!issue(cur, (int)(k & 1u), true)) return;
         }
-        if (pair == 0 && !peers_ready()) return;
       }
       for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++k) {
         // ---- rows of this tile have landed: form the proposal over the partner rows
@@ -505,19 +504,13 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
       if (tlk) tlk[5] = clock64() - t_entry;
     }
     if (h + 1 < nhalf) {
-      // this CTA's updates of half-step h are out: tell the grid -- and, multi-GPU, the last CTA of
-      // this rank tells every peer (consumer warps only, named barrier 1)
-      if (multi) __threadfence_system(); else __threadfence();
+      // this CTA's updates of half-step h are out: tell the grid (consumer warps only, named barrier 1)
+      __threadfence();
       asm volatile("bar.sync 1, %0;" ::"r"(32 * DMMA_CONSUMERS) : "memory");
       if (*sAbort) alive = false;
       if (tid == 0 && alive) {
-        if (multi) __threadfence_system(); else __threadfence();
-        const unsigned long long prev = atomicAdd(gbar, 1ull);
-        if (multi && prev == gbar_base + (unsigned long long)(h + 1) * gridDim.x - 1ull) {
-          __threadfence_system();
-          for (int r = 0; r < a.p2p_nranks; ++r)
-            if (r != a.p2p_rank) atomicExch_system(a.p2p_peer_flags[r] + a.p2p_rank, a.p2p_signal + (unsigned)h);
-        }
+        __threadfence();
+        atomicAdd(gbar, 1ull);
       }
     }
   }

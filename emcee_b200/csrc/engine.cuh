@@ -87,12 +87,13 @@ struct Engine;  // defined in capi.cu
 cudaError_t launch_split_tables(int32_t* order, const StepInfo* info_dev, int nsteps_chunk, int64_t N,
                                 uint64_t seed, uint64_t step0, int64_t w_lo, int64_t w_hi, int2* ranges,
                                 cudaStream_t st);
-// multi-GPU: for every (step, split) of the chunk, the active ranks [i_lo, i_hi) this rank owns, those whose
-// stretch partner lives on this rank first (stable) -- tiles built from the front need no NVLink traffic and no
-// peer barrier, so a half-step starts computing while the barrier and the first remote rows are still in flight
+// multi-GPU: for every (step, split) of the chunk, the active ranks [i_lo, i_hi) this rank owns with up to
+// front_cap walkers whose stretch partner lives on this rank moved to the front (stable) -- tiles built from the
+// front need no NVLink traffic and no peer barrier, so a half-step starts computing while the barrier and the
+// first remote rows are still in flight
 cudaError_t launch_locality_tables(const int32_t* order, const StepInfo* info_dev, const int2* ranges, int nsteps_chunk,
                                    int64_t N, uint64_t seed, uint64_t step0, int64_t rows_per_rank, int rank,
-                                   int32_t* aperm, cudaStream_t st);
+                                   int front_cap, int32_t* aperm, cudaStream_t st);
 cudaError_t launch_half_step_generic(int move_kind, const HalfStepArgs& a, cudaStream_t st);
 // TMA row-gather variant for the HBM-bound models (tma_rows.cu); *used == false: not applicable, use the generic one
 cudaError_t launch_half_step_tma(int move_kind, const HalfStepArgs& a, int sm_count, cudaStream_t st, bool* used);

@@ -107,10 +107,10 @@ __global__ void __launch_bounds__(TABLE_THREADS) locality_table_kernel(const int
                                                                        const StepInfo* __restrict__ info,
                                                                        const int2* __restrict__ ranges, int64_t N,
                                                                        uint64_t seed, uint64_t step0,
-                                                                       int64_t rows_per_rank, int rank,
+                                                                       int64_t rows_per_rank, int rank, int front_cap,
                                                                        int32_t* __restrict__ aperm_base) {
-  __shared__ int warp_cnt[2][32];
-  __shared__ int base_sh[2];
+  __shared__ int warp_cnt[2][32], loc_cnt[32];
+  __shared__ int base_sh[2], nfront_sh, seen_local_sh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = info[blockIdx.x].nsplits, split = blockIdx.y;
   if (split >= P) return;
@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(TABLE_THREADS) locality_table_kernel(const int
     const int64_t wp = order[r < a_start ? r : r + a_count];
     return wp / rows_per_rank == rank;
   };
-  // pass 1: how many owned active ranks have a local partner
+  // pass 1: how many owned active ranks have a local partner; at most `front_cap` of them (one tile per consumer
+  // warp of the grid: the first round) move to the front, the rest of the list keeps its natural mix of local
+  // and remote partners -- an all-remote tail would saturate the NVLink ports later instead
   int mine = 0;
   for (int i = i_lo + tid; i < i_hi; i += TABLE_THREADS) mine += is_local(i) ? 1 : 0;
   for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
@@ -138,32 +140,47 @@ __global__ void __launch_bounds__(TABLE_THREADS) locality_table_kernel(const int
   if (tid == 0) {
     int tot = 0;
     for (int k = 0; k < TABLE_THREADS / 32; ++k) tot += warp_cnt[0][k];
-    base_sh[0] = 0;    // next slot of the local group
-    base_sh[1] = tot;  // next slot of the remote group
+    nfront_sh = tot < front_cap ? tot : front_cap;
+    base_sh[0] = 0;          // next slot of the front group
+    base_sh[1] = nfront_sh;  // next slot of the rest
+    seen_local_sh = 0;       // local partners met so far (in natural order)
   }
   __syncthreads();
-  // pass 2: stable two-way partition, chunk by chunk
+  // pass 2: stable two-way partition, chunk by chunk: front = the first nfront local-partner walkers
   for (int c0 = i_lo; c0 < i_hi; c0 += TABLE_THREADS) {
     const int i = c0 + tid;
     const bool valid = i < i_hi;
     const bool loc = valid && is_local(i);
-    const unsigned bl = __ballot_sync(0xffffffffu, loc);
-    const unsigned br = __ballot_sync(0xffffffffu, valid && !loc);
+    // rank of this walker among the local-partner ones
+    const unsigned bloc = __ballot_sync(0xffffffffu, loc);
+    if (lane == 0) warp_cnt[0][warp] = __popc(bloc);
+    __syncthreads();
+    int lrank = seen_local_sh + __popc(bloc & ((1u << lane) - 1u));
+    for (int k = 0; k < warp; ++k) lrank += warp_cnt[0][k];
+    const bool front = loc && lrank < nfront_sh;
+    __syncthreads();
+    const unsigned bf = __ballot_sync(0xffffffffu, front);
+    const unsigned br = __ballot_sync(0xffffffffu, valid && !front);
     if (lane == 0) {
-      warp_cnt[0][warp] = __popc(bl);
+      warp_cnt[0][warp] = __popc(bf);
       warp_cnt[1][warp] = __popc(br);
+      loc_cnt[warp] = __popc(bloc);
     }
     __syncthreads();
     int off = 0;
-    const int grp = loc ? 0 : 1;
+    const int grp = front ? 0 : 1;
     for (int k = 0; k < warp; ++k) off += warp_cnt[grp][k];
-    const unsigned b = loc ? bl : br;
-    if (valid) aperm[a_start + base_sh[grp] + off + __popc(b & ((1u << lane) - 1u)) + i_lo] = i;
+    const unsigned b = front ? bf : br;
+    if (valid) aperm[a_start + i_lo + base_sh[grp] + off + __popc(b & ((1u << lane) - 1u))] = i;
     __syncthreads();
     if (tid < 2) {
       int tot = 0;
       for (int k = 0; k < TABLE_THREADS / 32; ++k) tot += warp_cnt[tid][k];
       base_sh[tid] += tot;
+    } else if (tid == 2) {
+      int tot = 0;
+      for (int k = 0; k < TABLE_THREADS / 32; ++k) tot += loc_cnt[k];
+      seen_local_sh += tot;
     }
     __syncthreads();
   }
@@ -171,9 +188,9 @@ __global__ void __launch_bounds__(TABLE_THREADS) locality_table_kernel(const int
 
 cudaError_t launch_locality_tables(const int32_t* order, const StepInfo* info_dev, const int2* ranges, int nsteps_chunk,
                                    int64_t N, uint64_t seed, uint64_t step0, int64_t rows_per_rank, int rank,
-                                   int32_t* aperm, cudaStream_t st) {
+                                   int front_cap, int32_t* aperm, cudaStream_t st) {
   locality_table_kernel<<<dim3(nsteps_chunk, MAX_SPLITS), TABLE_THREADS, 0, st>>>(order, info_dev, ranges, N, seed, step0,
-                                                                                 rows_per_rank, rank, aperm);
+                                                                                 rows_per_rank, rank, front_cap, aperm);
   return cudaGetLastError();
 }
 

@@ -37,6 +37,7 @@ __device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t step, uint32
 __global__ void __launch_bounds__(1024) cov_chol_kernel(const double* __restrict__ acc, double n, int D,
                                                         double* __restrict__ cov, double* __restrict__ L) {
   __shared__ double s_piv, s_tol;
+  __shared__ int s_left;  // pivots still allowed: rank(cov of n rows) <= n - 1
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int e = tid; e < D * D; e += nt) {
     const int r = e / D, c = e - r * D;
@@ -48,13 +49,15 @@ __global__ void __launch_bounds__(1024) cov_chol_kernel(const double* __restrict
     double m = 0.0;
     for (int j = 0; j < D; ++j) m = fmax(m, cov[(size_t)j * D + j]);
     s_tol = 1e-12 * m;
+    s_left = n - 1.0 < (double)D ? (int)(n - 1.0) : D;
   }
   __syncthreads();
   for (int j = 0; j < D; ++j) {
     if (tid == 0) {
       double d = cov[(size_t)j * D + j];
       for (int k = 0; k < j; ++k) d -= L[(size_t)j * D + k] * L[(size_t)j * D + k];
-      s_piv = d > s_tol ? sqrt(d) : 0.0;
+      s_piv = (s_left > 0 && d > s_tol) ? sqrt(d) : 0.0;
+      if (s_piv > 0.0) s_left -= 1;
       L[(size_t)j * D + j] = s_piv;
     }
     __syncthreads();
@@ -116,6 +119,7 @@ __global__ void __launch_bounds__(128) walk_subset_propose_kernel(const HalfStep
   double* L = cov + (size_t)D * D;   // [D * D]
   int32_t* ids = reinterpret_cast<int32_t*>(L + (size_t)D * D);  // [s0] helper walker ids
   __shared__ double s_piv, s_tol;
+  __shared__ int s_left;  // pivots still allowed: rank(cov of s0 rows) <= s0 - 1
   const int64_t i = blockIdx.x;
   const int64_t Nc = a.N - a.a_count;
   // walk.py:34  inds = random.choice(Nc, s, replace=False): first s images of the keyed permutation
@@ -166,13 +170,15 @@ __global__ void __launch_bounds__(128) walk_subset_propose_kernel(const HalfStep
     double m = 0.0;
     for (int j = 0; j < D; ++j) m = fmax(m, cov[j * D + j]);
     s_tol = 1e-12 * m;
+    s_left = s0 - 1 < D ? s0 - 1 : D;
   }
   __syncthreads();
   for (int j = 0; j < D; ++j) {
     if (tid == 0) {
       double d = cov[j * D + j];
       for (int k = 0; k < j; ++k) d -= L[j * D + k] * L[j * D + k];
-      s_piv = d > s_tol ? sqrt(d) : 0.0;
+      s_piv = (s_left > 0 && d > s_tol) ? sqrt(d) : 0.0;
+      if (s_piv > 0.0) s_left -= 1;
       L[j * D + j] = s_piv;
     }
     __syncthreads();

@@ -170,20 +170,27 @@ def normals(seed, step, split, index, count):
     return out
 
 
-def chol_psd(cov):
+def chol_psd(cov, max_rank=None):
     """Lower factor ``L`` with ``L L^T = cov`` for a positive SEMI-definite matrix: plain column
     Cholesky in which a pivot at or below ``1e-12 * max(diag)`` zeroes its column (for a PSD matrix the
-    rest of that column is zero as well).  This is the factorisation the draw specification fixes for
-    ``multivariate_normal(mean, cov) := mean + L z`` (numpy's own uses an SVD whose sign / ordering
-    conventions cannot be reproduced bit-for-bit by independent hardware)."""
+    rest of that column is zero as well), and which stops after ``max_rank`` pivots: the sample covariance
+    of ``s`` rows has rank at most ``s - 1``, and whatever a later pivot shows is rounding noise that a
+    small earlier pivot has amplified -- taking its square root would put O(1e-6) garbage into the factor.
+    This is the factorisation the draw specification fixes for ``multivariate_normal(mean, cov) := mean +
+    L z`` (numpy's own uses an SVD whose sign / ordering conventions cannot be reproduced bit-for-bit by
+    independent hardware)."""
     a = np.atleast_2d(np.asarray(cov, dtype=np.float64))
     n = a.shape[0]
     L = np.zeros_like(a)
     tol = 1e-12 * max(float(np.max(np.diag(a))), 0.0)
+    left = n if max_rank is None else int(max_rank)
     for j in range(n):
+        if left <= 0:
+            break
         d = a[j, j] - np.dot(L[j, :j], L[j, :j])
         if not d > tol:
             continue
+        left -= 1
         L[j, j] = np.sqrt(d)
         if j + 1 < n:
             L[j + 1 :, j] = (a[j + 1 :, j] - L[j + 1 :, :j] @ L[j, :j]) / L[j, j]
@@ -347,6 +354,7 @@ class PhiloxRandom(object):
             assert p is None
             self._open_split()
             out = subset_indices(self.seed, self._cur, self._split, self._i, int(a), int(size))
+            self._walk_rank = int(size) - 1  # rank bound of the covariance the next call receives
             self._log("walk_subset", out.copy())
             return out
         if isinstance(a, (int, np.integer)):
@@ -388,8 +396,8 @@ class PhiloxRandom(object):
 
     def multivariate_normal(self, mean, cov):
         mean = np.asarray(mean, dtype=np.float64)
-        L = chol_psd(cov)
         if self._phase in ("step", "mh"):
+            L = chol_psd(cov)
             # GaussianMove with a full covariance: ONE draw per step, added to every walker (gaussian.py:116-118)
             self._phase = "mh"
             z = normals(self.seed, self._cur, 0, np.array([0]), len(mean))[0]
@@ -397,6 +405,7 @@ class PhiloxRandom(object):
             return mean + L @ z
         # WalkMove: ``random.multivariate_normal(s[i], cov)`` for active rank i  (walk.py:36)
         assert self._phase == "proposal"
+        L = chol_psd(cov, max_rank=self._walk_rank)
         z = normals(self.seed, self._cur, self._split, np.array([self._i]), len(mean))[0]
         self._log("walk_z", z.copy())
         self._i += 1

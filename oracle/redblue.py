@@ -231,11 +231,11 @@ class OracleSampler(object):
         for i in range(Ns):
             if s0 == Nc:  # the whole complement, in its own order: one covariance for the split
                 if shared is None:
-                    shared = px.chol_psd(np.atleast_2d(np.cov(c, rowvar=0)))  # walk.py:35
+                    shared = px.chol_psd(np.atleast_2d(np.cov(c, rowvar=0)), max_rank=s0 - 1)  # walk.py:35
                 L = shared
             else:
                 inds = px.subset_indices(self.seed, step, split, i, Nc, s0)  # walk.py:34
-                L = px.chol_psd(np.atleast_2d(np.cov(c[inds], rowvar=0)))  # walk.py:35
+                L = px.chol_psd(np.atleast_2d(np.cov(c[inds], rowvar=0)), max_rank=s0 - 1)  # walk.py:35
             q[i] = s[i] + L @ z[i]  # walk.py:36 with multivariate_normal := mean + chol(cov) z
         self.taps = dict(z=z)
         return q, np.zeros(Ns, dtype=np.float64)  # walk.py:37

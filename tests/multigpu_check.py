@@ -8,8 +8,8 @@ Every rank steps the same global ensemble (row-block sharded) in both exchange
 modes and compares the result with the single-process oracle: stretch
 coordinates and accept counts bit-exact, log-probabilities to 1e-11 -- i.e. the
 result does not depend on the number of GPUs.  Covers the dense_dmma kernel
-(one launch per half-step with the fused peer barrier, and the persistent
-multi-half-step launch), tma_rows, the generic kernel, a mixed schedule that
+(one launch per half-step with the fused peer barrier, locality-sorted and natural tile
+order), tma_rows, the generic kernel, a mixed schedule that
 alternates fused and unfused kernels, stored chains, sharded read-back and the
 device-side chain moments."""
 import os
@@ -49,10 +49,11 @@ def compare(last_coords, last_lp, o, omoves, rows=slice(None)):
                                atol=1e-4 if snooker else 1e-11)
 
 
-def run_case(rdv, mode, name, N, D, omoves, dmoves, steps, seed=0xD157, group=1):
+def run_case(rdv, mode, name, N, D, omoves, dmoves, steps, seed=0xD157, group=1, local_first=1):
     s, target, p0 = build(rdv, mode, name, N, D, dmoves, seed)
     if group > 1:
         s._engine.set_option("dmma_group", group)
+    s._engine.set_option("dmma_local_first", local_first)
     last = s.run_mcmc(p0, steps, store=False, skip_initial_state_check=True)
     nacc = s._engine.naccepted()
     o = rb.OracleSampler(N, D, target, omoves, seed=seed)
@@ -133,14 +134,15 @@ def main():
         run_store_case(rdv, mode, "gauss_iso", 512, 8, [(S(), 0.6), (DE(), 0.4)],
                        [(moves.StretchMove(), 0.6), (moves.DEMove(), 0.4)], 5, 1)
         run_sharded_case(rdv, mode, 2048, 32, 6)
-    # persistent multi-half-step launch with the peer barrier between its half-steps (P2P only)
-    run_case(rdv, "p2p", "gauss_dense", 4096, 128, [(S(), 1.0)], moves.StretchMove(), 24, group=8)
+    # the option is accepted but sharded ensembles always run one half-step per launch
     run_case(rdv, "p2p", "gauss_dense", 1024, 24, [(S(nsplits=3), 1.0)], moves.StretchMove(nsplits=3), 16, group=5)
+    # natural tile order (peer barrier at the head of every half-step) as well as the locality-sorted default
+    run_case(rdv, "p2p", "gauss_dense", 4096, 128, [(S(), 1.0)], moves.StretchMove(), 24, local_first=0)
     if not QUICK:
-        # >= 4 tiles per consumer warp on every rank: the steady state of the two-deep landing pipeline
+        # >= 4 tiles per consumer warp on every rank: the steady state of the landing pipeline
         n_big = 8 * 148 * 8 * 4 * 2 * rdv.world
         run_case(rdv, "p2p", "gauss_dense", n_big, 128, [(S(), 1.0)], moves.StretchMove(), 3)
-        run_case(rdv, "p2p", "gauss_dense", n_big, 128, [(S(), 1.0)], moves.StretchMove(), 3, group=4)
+        run_case(rdv, "p2p", "gauss_dense", n_big, 128, [(S(), 1.0)], moves.StretchMove(), 3, local_first=0)
     if rdv.rank == 0:
         print("ALL MULTI-GPU CHECKS PASSED (world=%d)" % rdv.world, flush=True)
     rdv.close()
