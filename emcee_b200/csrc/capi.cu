@@ -80,7 +80,7 @@ struct eb_ctx {
   int dmma_stagger = 1;
   int dmma_group = 1;  // half-steps per persistent dense_dmma launch (1: a launch per half-step)
   int pdl = 1;           // dense_dmma launches chain as programmatic dependents (1: one GPU only, 2: sharded too)
-  bool local_first = true;  // sharded dense_dmma: tiles with local partners first, peer barrier deferred behind them
+  int local_first = 1;  // sharded dense_dmma: local-partner tiles first, peer barrier behind them (0 never, 1 auto, 2 always)
   bool chain_ok = false; // the last operation enqueued on the stream is a dense_dmma kernel of this run
   // multi-GPU: log_prob / accept mask / counters (and, P2P, coords) of rows owned by OTHER ranks are stale
   // on this rank until the next collective read (eb_get_state, eb_get_naccepted, ...) replicates them
@@ -851,6 +851,8 @@ int launch_step_gaussian(eb_ctx* c, const Schedule& s, size_t mi, uint64_t step,
   return EB_OK;
 }
 
+constexpr int DMMA_TILE_SLOTS = 8;  // consumer warps per SM of the dense_dmma kernel
+
 // a run of consecutive half-steps handed to ONE persistent dense_dmma launch
 struct DmmaGroup {
   size_t first = 0;  // index into the chunk's HalfDesc array
@@ -864,9 +866,13 @@ int flush_dmma(eb_ctx* c, const eb_move& mv, DmmaGroup& grp, uint64_t& launches)
   fill_base_args(c, mv, a);
   a.order = c->order;  // chunk base; HalfDesc::order_step selects the table
   a.range = c->comm.nranks > 1 ? c->comm.ranges : nullptr;
-  a.aperm = (c->comm.nranks > 1 && c->local_first) ? c->comm.aperm : nullptr;
   int bound = grp.max_count;
   if (c->comm.nranks > 1 && c->comm.rows_per_rank < bound) bound = (int)c->comm.rows_per_rank;
+  // Locality-sorted tiles hide the peer barrier and the first remote fetch behind local work, but move the
+  // remote burst to the second round: measured (profiles/r02_ab_2gpu.md) a gain when a consumer warp has
+  // at most ~2 tiles per half-step (strong scaling: +4 %) and a loss with long tile lists (weak: -4 %).
+  const bool few_tiles = (bound + 7) / 8 <= 2 * DMMA_TILE_SLOTS * c->sm_count;
+  a.aperm = (c->comm.nranks > 1 && (c->local_first == 2 || (c->local_first == 1 && few_tiles))) ? c->comm.aperm : nullptr;
   // P2P: the peer barrier rides inside the kernel (wait at its start, between its half-steps, signal at its end)
   const bool fused = comm_fuse_barrier(c->comm, a, grp.nhalf);
   c->fused_last = fused;
@@ -1424,7 +1430,7 @@ int eb_set_option(eb_ctx* c, const char* name, int64_t value) {
     return EB_OK;
   }
   if (!strcmp(name, "dmma_local_first")) {
-    c->local_first = value != 0;
+    c->local_first = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
     return EB_OK;
   }
   if (!strcmp(name, "pdl")) {

@@ -49,7 +49,7 @@ def compare(last_coords, last_lp, o, omoves, rows=slice(None)):
                                atol=1e-4 if snooker else 1e-11)
 
 
-def run_case(rdv, mode, name, N, D, omoves, dmoves, steps, seed=0xD157, group=1, local_first=1):
+def run_case(rdv, mode, name, N, D, omoves, dmoves, steps, seed=0xD157, group=1, local_first=2):
     s, target, p0 = build(rdv, mode, name, N, D, dmoves, seed)
     if group > 1:
         s._engine.set_option("dmma_group", group)
