@@ -393,7 +393,7 @@ def build_sampler(args, w, dist, gather_results=True, pinned=False):
     if args.no_tma_rows:
         eng.set_option("tma_rows", 0)
     if args.tma_rows:
-        eng.set_option("tma_rows", 1)
+        eng.set_option("tma_rows", args.tma_rows)
     if args.no_stagger:
         eng.set_option("dmma_stagger", 0)
     if args.no_pdl:
@@ -634,7 +634,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the short runs of BASELINE.json's other configurations")
     ap.add_argument("--no-microbench", action="store_true",
                     help="do not launch the fp64 peak micro-benchmarks (for ncu launch lists); use the recorded peak")
-    ap.add_argument("--tma-rows", action="store_true", help="force the tma_rows kernel on")
+    ap.add_argument("--tma-rows", type=int, default=0, help="tma_rows option value (1: short rows only, 2: long rows too)")
     ap.add_argument("--no-tma-rows", action="store_true", help="HBM-bound models: use the generic kernel instead of tma_rows")
     ap.add_argument("--no-stagger", action="store_true", help="dense_dmma: all pairs request their first tile at once")
     ap.add_argument("--no-pdl", action="store_true", help="dense_dmma: plain stream-ordered launches instead of programmatic dependent launches")

@@ -75,7 +75,7 @@ struct eb_ctx {
   uint64_t last_launches = 0;
   const char* last_kernel = "none";
   bool allow_dmma = true;
-  bool allow_tma = true;
+  int allow_tma = 2;  // TMA row-gather kernel for the HBM-bound models: 0 off, 1 short rows only, 2 long rows too
   bool fused_last = false;  // the last dense_dmma launch carried the P2P barrier itself
   int dmma_stagger = 1;
   int dmma_group = 1;  // half-steps per persistent dense_dmma launch (1: a launch per half-step)
@@ -186,7 +186,7 @@ int eb_create(int device, int64_t nwalkers, int64_t ndim, uint64_t seed, eb_ctx*
   c->N = nwalkers;
   c->D = (int)ndim;
   c->seed = seed;
-  if (const char* e = getenv("EMCEE_B200_TMA_ROWS")) c->allow_tma = atoi(e) != 0;  // developer override
+  if (const char* e = getenv("EMCEE_B200_TMA_ROWS")) c->allow_tma = atoi(e);  // developer override
   auto fail = [&](const char* what, cudaError_t err) {
     g_create_err = std::string("eb_create: ") + what + ": " + cudaGetErrorString(err);
     eb_destroy(c);
@@ -737,7 +737,8 @@ int launch_step_generic(eb_ctx* c, const eb_move& mv, uint64_t step, const int32
     }
     c->chain_ok = false;
     bool used_tma = false;
-    if (c->allow_tma && !c->debug) CK(c, launch_half_step_tma(mv.kind, a, c->sm_count, c->st, &used_tma));
+    if (c->allow_tma && !c->debug)
+      CK(c, launch_half_step_tma(mv.kind, a, c->sm_count, c->allow_tma >= 2, c->st, &used_tma));
     if (used_tma) {
       c->last_kernel = "tma_rows";
     } else {
@@ -1442,7 +1443,7 @@ int eb_set_option(eb_ctx* c, const char* name, int64_t value) {
     return moments_config(c, (uint64_t)value);
   }
   if (!strcmp(name, "tma_rows")) {
-    c->allow_tma = value != 0;
+    c->allow_tma = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
     return EB_OK;
   }
   if (!strcmp(name, "dense_dmma")) {

@@ -12,6 +12,11 @@
 // (completion on an mbarrier), accepted rows leave as ONE bulk store, and each warp runs a
 // two-stage pipeline: the rows of tile k+1 are in flight while tile k is computed.
 //
+// Per-walker scalar work (two or three Philox blocks, the logs of the accept test, Box-Muller, the pair
+// decode, the split-table lookups) is NOT done by the G lanes that share a walker's row: once per batch of
+// G tiles (= 32 walkers) every lane does it for ONE walker, and the tile loop fetches what it needs with
+// shuffles -- at 32-D that removes three quarters of the kernel's instructions (ncu: 964 -> ~500 per tile).
+//
 // Layout of a stage: [NR][R][D + G] doubles -- NR rows per walker (own + partners), R walkers
 // per tile, G = 32 / R lanes per walker; the G-double pad staggers consecutive walkers' rows
 // across the banks so a warp-wide access costs the minimum two wavefronts.
@@ -32,12 +37,13 @@ struct RowsPerWalker {
   static constexpr int value = MOVE == EB_MOVE_STRETCH ? 2 : (MOVE == EB_MOVE_DE ? 3 : 4);
 };
 
-// what one lane group keeps about its walker of a tile
+// what one LANE keeps about one walker of the current batch of G tiles
 struct WalkerMeta {
   int32_t w;       // active walker id, < 0 for the padding rows of a partial tile
   int32_t pw[3];   // partner walker ids (stretch: [0]; DE: p0, p1; snooker: z, z1, z2)
   double scalar;   // stretch: zz | DE: gamma
-  double u_acc;    // accept uniform
+  double factor;   // stretch: (ndim - 1) log zz (stretch.py:31); else 0 (snooker's comes from the data)
+  double log_u;    // log of the accept uniform (red_blue.py:100)
 };
 
 template <int MOVE, int MODEL>
@@ -45,7 +51,7 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
   constexpr int NR = RowsPerWalker<MOVE>::value;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D;
-  const int G = 32 / R;           // lanes per walker
+  const int G = 32 / R;           // lanes per walker = tiles per batch
   const int RS = D + G;           // padded row stride (doubles)
   const int stage_doubles = NR * R * RS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -66,21 +72,25 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
   const int i_hi = a.range ? a.range->y : a.i_hi;
   const int64_t ntiles = ((int64_t)i_hi - i_lo + R - 1) / R;
   const int64_t tstride = (int64_t)gridDim.x * nwarps;
+  const int64_t tile_first = (int64_t)blockIdx.x + (int64_t)gridDim.x * warp;  // SM-major deal, as dense_dmma
   const int64_t Nc = a.N - a.a_count;
   const unsigned row_bytes = (unsigned)(D * sizeof(double));
 
-  // ---- draws and index lookups of this lane group's walker in one tile -------------------
-  auto prep = [&](int64_t tile) -> WalkerMeta {
+  // ---- draws and index lookups: lane l does walker (l % R) of tile (l / R) of batch kb -----------------
+  auto prep_batch = [&](int64_t kb) -> WalkerMeta {
     WalkerMeta m;
-    int64_t i = (int64_t)i_lo + tile * R + grp;
-    const bool valid = i < i_hi;
+    const int64_t tile = tile_first + (kb * G + lane / R) * tstride;
+    int64_t i = (int64_t)i_lo + tile * R + (lane % R);
+    const bool valid = tile < ntiles && i < i_hi;
     if (!valid) i = (int64_t)i_hi - 1;
     const u32x4 A = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_PROP_A, (uint32_t)i);
     m.pw[0] = m.pw[1] = m.pw[2] = 0;
     m.scalar = 0.0;
+    m.factor = 0.0;
     if (MOVE == EB_MOVE_STRETCH) {
       const double t = __dadd_rn(__dmul_rn(__dsub_rn(a.p0, 1.0), u53(A.x, A.y)), 1.0);  // stretch.py:30
       m.scalar = __ddiv_rn(__dmul_rn(t, t), a.p0);
+      m.factor = __dmul_rn((double)D - 1.0, log(m.scalar));  // stretch.py:31
       const int64_t r = (int64_t)bounded64(A.z, A.w, (uint64_t)Nc);  // stretch.py:32
       m.pw[0] = __ldg(a.order + (r < a.a_start ? r : r + a.a_count));
     } else if (MOVE == EB_MOVE_DE) {
@@ -109,55 +119,67 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
     const int32_t w = __ldg(a.order + a.a_start + i);
     m.w = valid ? w : -(w + 1);  // keep the id (its rows are still fetched), flag it as padding
     const u32x4 U = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_ACCEPT, (uint32_t)i);
-    m.u_acc = u53(U.x, U.y);
+    m.log_u = log(u53(U.x, U.y));
     return m;
   };
-  // ---- launch the NR * R row copies of a tile into a stage ----------------------------------
-  auto issue = [&](const WalkerMeta& m, int stage) {
+  // ---- launch the NR * R row copies of tile tb of a batch into a stage ---------------------------------
+  auto issue = [&](const WalkerMeta& m, int tb, int stage) {
     double* buf = wbuf + (size_t)stage * stage_doubles;
     if (lane == 0) mbar_arrive_expect_tx(bars + stage, (unsigned)(NR * R) * row_bytes);
     __syncwarp();
-    // copy c (< NR*R <= 32) is row j = c / R of walker r = c % R; its ids live in lane r*G
+    // copy c (< NR*R <= 32) is row j = c / R of walker r = c % R; its ids live in lane tb * R + r
     const int c = lane, j = c / R, r = c % R;
+    const int src = (tb * R + r) & 31;
     const int wself = m.w >= 0 ? m.w : -(m.w + 1);
-    const int src_self = __shfl_sync(0xffffffffu, wself, (r * G) & 31);
-    const int src_p0 = __shfl_sync(0xffffffffu, m.pw[0], (r * G) & 31);
-    const int src_p1 = __shfl_sync(0xffffffffu, m.pw[1], (r * G) & 31);
-    const int src_p2 = __shfl_sync(0xffffffffu, m.pw[2], (r * G) & 31);
+    const int src_self = __shfl_sync(0xffffffffu, wself, src);
+    const int src_p0 = __shfl_sync(0xffffffffu, m.pw[0], src);
+    const int src_p1 = __shfl_sync(0xffffffffu, m.pw[1], src);
+    const int src_p2 = __shfl_sync(0xffffffffu, m.pw[2], src);
     if (c < NR * R) {
       const int64_t wr = j == 0 ? src_self : (j == 1 ? src_p0 : (j == 2 ? src_p1 : src_p2));
-      const double* src = (j == 0) ? a.coords + (size_t)wr * D : row_ptr(a, wr);
-      bulk_g2s(buf + ((size_t)j * R + r) * RS, src, row_bytes, bars + stage);
+      const double* srcp = (j == 0) ? a.coords + (size_t)wr * D : row_ptr(a, wr);
+      bulk_g2s(buf + ((size_t)j * R + r) * RS, srcp, row_bytes, bars + stage);
     }
   };
 
-  int64_t tile = (int64_t)blockIdx.x + (int64_t)gridDim.x * warp;  // SM-major deal, as dense_dmma
-  WalkerMeta cur{}, nxt{};
-  if (tile < ntiles) {
-    cur = prep(tile);
-    issue(cur, 0);
+  // this warp's k-th tile is tile_first + k * tstride; tiles come in batches of G (one walker per lane)
+  WalkerMeta batch{}, batch_next{};
+  if (tile_first < ntiles) {
+    batch = prep_batch(0);
+    issue(batch, 0, 0);
   }
   unsigned k = 0;
-  for (; tile < ntiles; tile += tstride, ++k) {
+  for (int64_t tile = tile_first; tile < ntiles; tile += tstride, ++k) {
     const int stage = (int)(k & 1u);
+    const int tb = (int)(k % (unsigned)G);
     double* buf = wbuf + (size_t)stage * stage_doubles;
     const bool has_next = tile + tstride < ntiles;
     if (has_next) {
-      nxt = prep(tile + tstride);
+      const bool crosses = tb + 1 == G;  // the next tile opens a new batch: tabulate it first
+      if (crosses) batch_next = prep_batch((int64_t)(k + 1) / G);
       bulk_wait_read();  // the accepted rows of tile k-1 have left the other stage
       __syncwarp();
-      issue(nxt, stage ^ 1);
+      if (crosses)
+        issue(batch_next, 0, stage ^ 1);
+      else
+        issue(batch, tb + 1, stage ^ 1);
     }
+    // this group's walker: scalars from the lane that tabulated it
+    const int me = (tb * R + grp) & 31;
+    const int32_t cur_w = __shfl_sync(0xffffffffu, batch.w, me);
+    const double cur_scalar = __shfl_sync(0xffffffffu, batch.scalar, me);
+    const double cur_factor = __shfl_sync(0xffffffffu, batch.factor, me);
+    const double cur_log_u = __shfl_sync(0xffffffffu, batch.log_u, me);
     mbar_wait(bars + stage, (k >> 1) & 1u);
 
     double* s = buf + ((size_t)0 * R + grp) * RS;  // own row, overwritten by the proposal
-    const bool valid = cur.w >= 0;
-    const int64_t w = valid ? cur.w : -(cur.w + 1);
-    double factor = 0.0;
+    const bool valid = cur_w >= 0;
+    const int64_t w = valid ? cur_w : -(cur_w + 1);
+    double factor = cur_factor;
 
     if (MOVE == EB_MOVE_STRETCH) {
       const double* c = buf + ((size_t)1 * R + grp) * RS;
-      const double zz = cur.scalar;
+      const double zz = cur_scalar;
       for (int e = g; e < D; e += G) {
         const double sv = s[e], cv = c[e];
         // stretch.py:33  q = c - (c - s) * zz   (each op rounded once, no FMA contraction)
@@ -165,11 +187,10 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
         s[e] = v;
         if (!isfinite(v)) flag_nonfinite(v, a.status);
       }
-      factor = __dmul_rn((double)D - 1.0, log(zz));  // stretch.py:31
     } else if (MOVE == EB_MOVE_DE) {
       const double* c0 = buf + ((size_t)1 * R + grp) * RS;
       const double* c1 = buf + ((size_t)2 * R + grp) * RS;
-      const double gamma = cur.scalar;
+      const double gamma = cur_scalar;
       for (int e = g; e < D; e += G) {
         // de.py:53,62  q = s + gamma * (c[p1] - c[p0])
         const double v = __dadd_rn(s[e], __dmul_rn(gamma, __dsub_rn(c1[e], c0[e])));
@@ -215,7 +236,7 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
     if (isnan(lp_new) && g == 0) atomicOr(a.status, FLAG_NAN_LOGPROB);
     // red_blue.py:96-101
     const double lnpdiff = __dsub_rn(__dadd_rn(factor, lp_new), a.logp[w]);
-    const bool acc = valid && (lnpdiff > log(cur.u_acc));
+    const bool acc = valid && (lnpdiff > cur_log_u);
     // red_blue.py:103-104 -> move.py:29-34: one bulk store per accepted row
     fence_async_smem();
     __syncwarp();
@@ -228,26 +249,24 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
       if (valid) a.accepted[w] = acc ? 1 : 0;
     }
     bulk_commit();
-    cur = nxt;
+    if (tb + 1 == G) batch = batch_next;
   }
   // every accepted row has left shared memory AND reached global memory before the warp retires
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 template <int MOVE, int MODEL>
-cudaError_t launch_tma_t(const HalfStepArgs& a, int sm_count, cudaStream_t st, bool* used) {
+cudaError_t launch_tma_t(const HalfStepArgs& a, int sm_count, bool long_rows, cudaStream_t st, bool* used) {
   constexpr int NR = RowsPerWalker<MOVE>::value;
   *used = false;
   const int D = a.D;
   if (D % 2 != 0) return cudaSuccess;  // rows must be multiples of 16 bytes for bulk copies
-  // Latency is hidden by warps: 16 per SM, each with a 12 KB share of shared memory for its two
-  // stages; walkers per tile R = the largest power of two with NR*R <= 32 copies per stage that
-  // fits.  Measured (profiles/r01_tma_rows_ab.txt): with R >= 2 this kernel beats the generic one
-  // (ring 262144x32 +9 %, iso 65536x128 +18 %); for rows so long that only one walker per tile
-  // (or only 8 warps) fits -- e.g. 256-D DE/snooker -- the generic kernel is 23 % faster, so
-  // those shapes stay there.
+  // Latency is hidden by warps: 16 per SM when each one's two stages fit a 12 KB share of shared memory;
+  // walkers per tile R = the largest power of two with NR*R <= 32 copies per stage that fits.  Rows so long
+  // that only one walker per tile fits (e.g. 256-D DE / snooker) run with R = 1 and as many warps (>= 8) as
+  // 200 KB hold -- `long_rows`; measured against the generic kernel in profiles/r02_hbm_kernels.md.
   auto warp_bytes = [&](int r) { return (size_t)2 * NR * r * (D + 32 / r) * sizeof(double); };
-  const int nwarps = 16;
+  int nwarps = 16;
   const size_t budget = (size_t)192 * 1024 / nwarps;
   int R = 0;
   for (int r = 16; r >= 2; r >>= 1)
@@ -255,6 +274,13 @@ cudaError_t launch_tma_t(const HalfStepArgs& a, int sm_count, cudaStream_t st, b
       R = r;
       break;
     }
+  if (R == 0 && long_rows) {
+    const size_t fit = ((size_t)200 * 1024) / warp_bytes(1);
+    if (fit >= 8) {
+      R = 1;
+      nwarps = (int)(fit < 16 ? fit : 16);
+    }
+  }
   if (R == 0) return cudaSuccess;  // generic kernel
   const size_t smem = (size_t)nwarps * warp_bytes(R) + (size_t)nwarps * 2 * sizeof(uint64_t);
   const int64_t count = (int64_t)a.i_hi - a.i_lo;
@@ -274,14 +300,14 @@ cudaError_t launch_tma_t(const HalfStepArgs& a, int sm_count, cudaStream_t st, b
 }
 
 template <int MOVE>
-cudaError_t launch_tma_m(const HalfStepArgs& a, int sm_count, cudaStream_t st, bool* used) {
+cudaError_t launch_tma_m(const HalfStepArgs& a, int sm_count, bool long_rows, cudaStream_t st, bool* used) {
   switch (a.model.kind) {
     case EB_MODEL_GAUSS_ISO:
-      return launch_tma_t<MOVE, EB_MODEL_GAUSS_ISO>(a, sm_count, st, used);
+      return launch_tma_t<MOVE, EB_MODEL_GAUSS_ISO>(a, sm_count, long_rows, st, used);
     case EB_MODEL_ROSENBROCK:
-      return launch_tma_t<MOVE, EB_MODEL_ROSENBROCK>(a, sm_count, st, used);
+      return launch_tma_t<MOVE, EB_MODEL_ROSENBROCK>(a, sm_count, long_rows, st, used);
     case EB_MODEL_RING:
-      return launch_tma_t<MOVE, EB_MODEL_RING>(a, sm_count, st, used);
+      return launch_tma_t<MOVE, EB_MODEL_RING>(a, sm_count, long_rows, st, used);
   }
   *used = false;  // dense Gaussian outside the DMMA envelope: CUDA-core generic kernel
   return cudaSuccess;
@@ -291,14 +317,15 @@ cudaError_t launch_tma_m(const HalfStepArgs& a, int sm_count, cudaStream_t st, b
 
 // Tries the TMA row-gather kernel; *used tells whether it took the half-step (otherwise the
 // caller falls back to half_step_generic_kernel).
-cudaError_t launch_half_step_tma(int move_kind, const HalfStepArgs& a, int sm_count, cudaStream_t st, bool* used) {
+cudaError_t launch_half_step_tma(int move_kind, const HalfStepArgs& a, int sm_count, bool long_rows, cudaStream_t st,
+                                 bool* used) {
   switch (move_kind) {
     case EB_MOVE_STRETCH:
-      return launch_tma_m<EB_MOVE_STRETCH>(a, sm_count, st, used);
+      return launch_tma_m<EB_MOVE_STRETCH>(a, sm_count, long_rows, st, used);
     case EB_MOVE_DE:
-      return launch_tma_m<EB_MOVE_DE>(a, sm_count, st, used);
+      return launch_tma_m<EB_MOVE_DE>(a, sm_count, long_rows, st, used);
     case EB_MOVE_SNOOKER:
-      return launch_tma_m<EB_MOVE_SNOOKER>(a, sm_count, st, used);
+      return launch_tma_m<EB_MOVE_SNOOKER>(a, sm_count, long_rows, st, used);
   }
   *used = false;
   return cudaErrorInvalidValue;

@@ -210,8 +210,8 @@ int eb_debug_taps(eb_ctx* ctx, int64_t* partners, double* scalar, double* u_acce
 int eb_debug_timeline(eb_ctx* ctx, int64_t* out, size_t capacity, size_t* written);
 /* engine options: "debug_taps" (0/1: record the draws of each half-step for
  * eb_debug_taps; forces the generic kernel), "dense_dmma" (0/1: allow the
- * FP64 tensor-core kernel for stretch + gauss_dense; default 1), "tma_rows" (0/1: allow the TMA row-gather kernel
- * for the HBM-bound models; default 1), "dmma_stagger" (0/1: staggered
+ * FP64 tensor-core kernel for stretch + gauss_dense; default 1), "tma_rows" (0/1/2: the TMA row-gather kernel
+ * for the HBM-bound models: off / rows short enough for several walkers per tile / any even ndim; default 2), "dmma_stagger" (0/1: staggered
  * first tiles at launch start; default 1), "dmma_group" (n >= 1: half-steps
  * fused into one persistent cooperative launch of that kernel, separated by an
  * in-kernel grid barrier -- and, on a P2P-sharded ensemble, a peer-flag barrier; default 1), "pdl" (0/1/2: consecutive dense_dmma launches chain as programmatic
