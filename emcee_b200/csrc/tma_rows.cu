@@ -44,9 +44,14 @@ struct WalkerMeta {
   double scalar;   // stretch: zz | DE: gamma
   double factor;   // stretch: (ndim - 1) log zz (stretch.py:31); else 0 (snooker's comes from the data)
   double log_u;    // log of the accept uniform (red_blue.py:100)
+  double lp_old;   // current log-prob of the walker (red_blue.py:99); only this warp ever updates it
 };
 
-template <int MOVE, int MODEL>
+// EPL == 8: every lane owns 8 CONTIGUOUS elements of its walker's row (ndim == 8 * lanes per walker, which
+// covers 32-D at 8 walkers per tile, 128-D at 2, 256-D at 1): rows are read with 16-byte shared-memory loads
+// into registers, the proposal, the log-probability and the snooker norms run on registers with fully
+// unrolled loops.  EPL == 0: any even ndim, strided elements, run-time loops.
+template <int MOVE, int MODEL, int EPL>
 __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const HalfStepArgs a, const int R) {
   constexpr int NR = RowsPerWalker<MOVE>::value;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -120,6 +125,7 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
     m.w = valid ? w : -(w + 1);  // keep the id (its rows are still fetched), flag it as padding
     const u32x4 U = draw_words(a.seed, a.step, (uint32_t)a.split, TAG_ACCEPT, (uint32_t)i);
     m.log_u = log(u53(U.x, U.y));
+    m.lp_old = a.logp[w];
     return m;
   };
   // ---- launch the NR * R row copies of tile tb of a batch into a stage ---------------------------------
@@ -170,6 +176,7 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
     const double cur_scalar = __shfl_sync(0xffffffffu, batch.scalar, me);
     const double cur_factor = __shfl_sync(0xffffffffu, batch.factor, me);
     const double cur_log_u = __shfl_sync(0xffffffffu, batch.log_u, me);
+    const double cur_lp_old = __shfl_sync(0xffffffffu, batch.lp_old, me);
     mbar_wait(bars + stage, (k >> 1) & 1u);
 
     double* s = buf + ((size_t)0 * R + grp) * RS;  // own row, overwritten by the proposal
@@ -177,65 +184,167 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
     const int64_t w = valid ? cur_w : -(cur_w + 1);
     double factor = cur_factor;
 
-    if (MOVE == EB_MOVE_STRETCH) {
-      const double* c = buf + ((size_t)1 * R + grp) * RS;
-      const double zz = cur_scalar;
-      for (int e = g; e < D; e += G) {
-        const double sv = s[e], cv = c[e];
-        // stretch.py:33  q = c - (c - s) * zz   (each op rounded once, no FMA contraction)
-        const double v = __dsub_rn(cv, __dmul_rn(__dsub_rn(cv, sv), zz));
-        s[e] = v;
-        if (!isfinite(v)) flag_nonfinite(v, a.status);
+    double lp_new;
+    if constexpr (EPL == 8) {
+      // ---------------- register path: this lane's elements are [8 g, 8 g + 8) ----------------
+      auto ld8 = [&](const double* row, double (&v)[8]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double2 t2 = *reinterpret_cast<const double2*>(row + 8 * g + 2 * k);
+          v[2 * k] = t2.x;
+          v[2 * k + 1] = t2.y;
+        }
+      };
+      double q[8];
+      if (MOVE == EB_MOVE_STRETCH) {
+        double sv[8], cv[8];
+        ld8(s, sv);
+        ld8(buf + ((size_t)1 * R + grp) * RS, cv);
+        const double zz = cur_scalar;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)  // stretch.py:33  q = c - (c - s) * zz   (each op rounded once)
+          q[e] = __dsub_rn(cv[e], __dmul_rn(__dsub_rn(cv[e], sv[e]), zz));
+      } else if (MOVE == EB_MOVE_DE) {
+        double sv[8], c0[8], c1[8];
+        ld8(s, sv);
+        ld8(buf + ((size_t)1 * R + grp) * RS, c0);
+        ld8(buf + ((size_t)2 * R + grp) * RS, c1);
+        const double gamma = cur_scalar;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)  // de.py:53,62  q = s + gamma * (c[p1] - c[p0])
+          q[e] = __dadd_rn(sv[e], __dmul_rn(gamma, __dsub_rn(c1[e], c0[e])));
+      } else {
+        double sv[8], zv[8], u[8];
+        ld8(s, sv);
+        ld8(buf + ((size_t)1 * R + grp) * RS, zv);
+        double n2 = 0.0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          u[e] = __dsub_rn(sv[e], zv[e]);  // de_snooker.py:41
+          n2 = fma(u[e], u[e], n2);
+        }
+        const double norm = sqrt(group_sum(n2, G, mask));  // de_snooker.py:42
+        double d1 = 0.0, d2 = 0.0;
+        {
+          double z1[8], z2[8];
+          ld8(buf + ((size_t)2 * R + grp) * RS, z1);
+          ld8(buf + ((size_t)3 * R + grp) * RS, z2);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            u[e] = __ddiv_rn(u[e], norm);  // de_snooker.py:43
+            d1 = fma(u[e], z1[e], d1);
+            d2 = fma(u[e], z2[e], d2);
+          }
+        }
+        d1 = group_sum(d1, G, mask);
+        d2 = group_sum(d2, G, mask);
+        const double dd = __dsub_rn(d1, d2);
+        double m2 = 0.0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          // de_snooker.py:44  q = s + u * gammas * (u.z1 - u.z2)
+          q[e] = __dadd_rn(sv[e], __dmul_rn(__dmul_rn(u[e], a.p0), dd));
+          const double dq = __dsub_rn(q[e], zv[e]);
+          m2 = fma(dq, dq, m2);
+        }
+        const double qn = sqrt(group_sum(m2, G, mask));
+        factor = __dmul_rn((double)D - 1.0, __dsub_rn(log(qn), log(norm)));  // de_snooker.py:45-46
       }
-    } else if (MOVE == EB_MOVE_DE) {
-      const double* c0 = buf + ((size_t)1 * R + grp) * RS;
-      const double* c1 = buf + ((size_t)2 * R + grp) * RS;
-      const double gamma = cur_scalar;
-      for (int e = g; e < D; e += G) {
-        // de.py:53,62  q = s + gamma * (c[p1] - c[p0])
-        const double v = __dadd_rn(s[e], __dmul_rn(gamma, __dsub_rn(c1[e], c0[e])));
-        s[e] = v;
-        if (!isfinite(v)) flag_nonfinite(v, a.status);
+      bool bad = false;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bad |= !isfinite(q[e]);
+      if (bad) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) flag_nonfinite(q[e], a.status);  // ensemble.py:476-479
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)  // the proposal replaces the own row: source of the bulk store
+        *reinterpret_cast<double2*>(s + 8 * g + 2 * k) = make_double2(q[2 * k], q[2 * k + 1]);
+      // red_blue.py:93 -> ensemble.py:458-553: the registered models on registers (lane-sequential partial sums,
+      // then the xor-shuffle reduction over the walker's lanes: the order depends only on ndim)
+      double acc = 0.0;
+      if (MODEL == EB_MODEL_GAUSS_ISO || MODEL == EB_MODEL_RING) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc = fma(q[e], q[e], acc);
+        acc = group_sum(acc, G, mask);
+        if (MODEL == EB_MODEL_GAUSS_ISO) {
+          lp_new = -0.5 * acc;
+        } else {
+          const double d = sqrt(acc) - a.model.s0;
+          lp_new = -(d * d) / (2.0 * a.model.s1 * a.model.s1);
+        }
+      } else {  // EB_MODEL_ROSENBROCK: the successor of this lane's last element lives in the next lane
+        const double nxt = __shfl_down_sync(mask, q[0], 1);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const double x0 = q[e], x1 = e < 7 ? q[e < 7 ? e + 1 : 7] : nxt;
+          const double t1 = x1 - x0 * x0;
+          const double u1 = a.model.s0 - x0;
+          if (e < 7 || g + 1 < G) acc += a.model.s1 * (t1 * t1) + u1 * u1;
+        }
+        lp_new = -group_sum(acc, G, mask);
       }
     } else {
-      const double* z = buf + ((size_t)1 * R + grp) * RS;
-      double* z1 = buf + ((size_t)2 * R + grp) * RS;  // becomes u
-      const double* z2 = buf + ((size_t)3 * R + grp) * RS;
-      double n2 = 0.0;
-      for (int e = g; e < D; e += G) {
-        const double d = __dsub_rn(s[e], z[e]);  // de_snooker.py:41
-        n2 = fma(d, d, n2);
+      if (MOVE == EB_MOVE_STRETCH) {
+        const double* c = buf + ((size_t)1 * R + grp) * RS;
+        const double zz = cur_scalar;
+        for (int e = g; e < D; e += G) {
+          const double sv = s[e], cv = c[e];
+          // stretch.py:33  q = c - (c - s) * zz   (each op rounded once, no FMA contraction)
+          const double v = __dsub_rn(cv, __dmul_rn(__dsub_rn(cv, sv), zz));
+          s[e] = v;
+          if (!isfinite(v)) flag_nonfinite(v, a.status);
+        }
+      } else if (MOVE == EB_MOVE_DE) {
+        const double* c0 = buf + ((size_t)1 * R + grp) * RS;
+        const double* c1 = buf + ((size_t)2 * R + grp) * RS;
+        const double gamma = cur_scalar;
+        for (int e = g; e < D; e += G) {
+          // de.py:53,62  q = s + gamma * (c[p1] - c[p0])
+          const double v = __dadd_rn(s[e], __dmul_rn(gamma, __dsub_rn(c1[e], c0[e])));
+          s[e] = v;
+          if (!isfinite(v)) flag_nonfinite(v, a.status);
+        }
+      } else {
+        const double* z = buf + ((size_t)1 * R + grp) * RS;
+        double* z1 = buf + ((size_t)2 * R + grp) * RS;  // becomes u
+        const double* z2 = buf + ((size_t)3 * R + grp) * RS;
+        double n2 = 0.0;
+        for (int e = g; e < D; e += G) {
+          const double d = __dsub_rn(s[e], z[e]);  // de_snooker.py:41
+          n2 = fma(d, d, n2);
+        }
+        const double norm = sqrt(group_sum(n2, G, mask));  // de_snooker.py:42
+        double d1 = 0.0, d2 = 0.0;
+        for (int e = g; e < D; e += G) {
+          const double u = __ddiv_rn(__dsub_rn(s[e], z[e]), norm);  // de_snooker.py:43
+          d1 = fma(u, z1[e], d1);
+          d2 = fma(u, z2[e], d2);
+          z1[e] = u;
+        }
+        d1 = group_sum(d1, G, mask);
+        d2 = group_sum(d2, G, mask);
+        const double dd = __dsub_rn(d1, d2);
+        double m2 = 0.0;
+        for (int e = g; e < D; e += G) {
+          // de_snooker.py:44  q = s + u * gammas * (u.z1 - u.z2)
+          const double v = __dadd_rn(s[e], __dmul_rn(__dmul_rn(z1[e], a.p0), dd));
+          s[e] = v;
+          if (!isfinite(v)) flag_nonfinite(v, a.status);
+          const double dq = __dsub_rn(v, z[e]);
+          m2 = fma(dq, dq, m2);
+        }
+        const double qn = sqrt(group_sum(m2, G, mask));
+        factor = __dmul_rn((double)D - 1.0, __dsub_rn(log(qn), log(norm)));  // de_snooker.py:45-46
       }
-      const double norm = sqrt(group_sum(n2, G, mask));  // de_snooker.py:42
-      double d1 = 0.0, d2 = 0.0;
-      for (int e = g; e < D; e += G) {
-        const double u = __ddiv_rn(__dsub_rn(s[e], z[e]), norm);  // de_snooker.py:43
-        d1 = fma(u, z1[e], d1);
-        d2 = fma(u, z2[e], d2);
-        z1[e] = u;
-      }
-      d1 = group_sum(d1, G, mask);
-      d2 = group_sum(d2, G, mask);
-      const double dd = __dsub_rn(d1, d2);
-      double m2 = 0.0;
-      for (int e = g; e < D; e += G) {
-        // de_snooker.py:44  q = s + u * gammas * (u.z1 - u.z2)
-        const double v = __dadd_rn(s[e], __dmul_rn(__dmul_rn(z1[e], a.p0), dd));
-        s[e] = v;
-        if (!isfinite(v)) flag_nonfinite(v, a.status);
-        const double dq = __dsub_rn(v, z[e]);
-        m2 = fma(dq, dq, m2);
-      }
-      const double qn = sqrt(group_sum(m2, G, mask));
-      factor = __dmul_rn((double)D - 1.0, __dsub_rn(log(qn), log(norm)));  // de_snooker.py:45-46
-    }
-    __syncwarp(mask);
+      __syncwarp(mask);
 
-    // red_blue.py:93 -> ensemble.py:458-553
-    const double lp_new = model_logprob<MODEL>(s, nullptr, D, g, G, mask, a.model);
+      // red_blue.py:93 -> ensemble.py:458-553
+      lp_new = model_logprob<MODEL>(s, nullptr, D, g, G, mask, a.model);
+    }
     if (isnan(lp_new) && g == 0) atomicOr(a.status, FLAG_NAN_LOGPROB);
     // red_blue.py:96-101
-    const double lnpdiff = __dsub_rn(__dadd_rn(factor, lp_new), a.logp[w]);
+    const double lnpdiff = __dsub_rn(__dadd_rn(factor, lp_new), cur_lp_old);
     const bool acc = valid && (lnpdiff > cur_log_u);
     // red_blue.py:103-104 -> move.py:29-34: one bulk store per accepted row
     fence_async_smem();
@@ -288,7 +397,8 @@ cudaError_t launch_tma_t(const HalfStepArgs& a, int sm_count, bool long_rows, cu
     *used = true;
     return cudaSuccess;
   }
-  auto kern = half_step_tma_kernel<MOVE, MODEL>;
+  const bool epl8 = D == 8 * (32 / R);  // 8 contiguous elements per lane: the register path
+  auto kern = epl8 ? half_step_tma_kernel<MOVE, MODEL, 8> : half_step_tma_kernel<MOVE, MODEL, 0>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t ntiles = (count + R - 1) / R;

@@ -23,7 +23,7 @@ FULL = [
     ("gauss_dense", 40008, 128, [(rb.Stretch(nsplits=3), 1.0)], 2, "dense_dmma"),
     ("ring", 262144, 32, [(rb.Stretch(), 1.0)], 2, "tma_rows"),
     ("gauss_iso", 65536, 128, [(rb.Stretch(a=1.7), 1.0)], 2, "tma_rows"),
-    ("rosenbrock", 16384, 256, [(rb.DE(), 0.8), (rb.Snooker(), 0.2)], 3, "generic"),
+    ("rosenbrock", 16384, 256, [(rb.DE(), 0.8), (rb.Snooker(), 0.2)], 3, "tma_rows"),
 ]
 
 
