@@ -286,7 +286,8 @@ bool walk_subset_supported(int D, int s0) { return D <= WALK_MAX_D && s0 <= WALK
 
 cudaError_t launch_walk_subset_propose(const HalfStepArgs& a, int s0, double* qbuf, cudaStream_t st) {
   if (a.a_count <= 0) return cudaSuccess;
-  const size_t smem = ((size_t)2 * a.D + (size_t)2 * a.D * a.D) * sizeof(double) + (size_t)s0 * sizeof(int32_t);
+  // (+8: the compiler reads helper ids in pairs, so an odd count touches one id past the end)
+  const size_t smem = ((size_t)2 * a.D + (size_t)2 * a.D * a.D) * sizeof(double) + (size_t)s0 * sizeof(int32_t) + 8;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(walk_subset_propose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -47,10 +47,11 @@ struct WalkerMeta {
   double lp_old;   // current log-prob of the walker (red_blue.py:99); only this warp ever updates it
 };
 
-// EPL == 8: every lane owns 8 CONTIGUOUS elements of its walker's row (ndim == 8 * lanes per walker, which
-// covers 32-D at 8 walkers per tile, 128-D at 2, 256-D at 1): rows are read with 16-byte shared-memory loads
-// into registers, the proposal, the log-probability and the snooker norms run on registers with fully
-// unrolled loops.  EPL == 0: any even ndim, strided elements, run-time loops.
+// EPL == 8: every lane owns 8 elements of its walker's row as four 16-byte chunks interleaved over the
+// walker's lanes (chunk g + G k, k = 0..3: consecutive lanes read consecutive 16 bytes, no bank conflicts);
+// needs ndim == 8 * lanes per walker, which covers 32-D at 8 walkers per tile, 128-D at 2, 256-D at 1.  Rows
+// are read with 16-byte shared-memory loads into registers; the proposal, the log-probability and the snooker
+// norms run on registers with fully unrolled loops.  EPL == 0: any even ndim, strided elements, run-time loops.
 template <int MOVE, int MODEL, int EPL>
 __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const HalfStepArgs a, const int R) {
   constexpr int NR = RowsPerWalker<MOVE>::value;
@@ -186,11 +187,11 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
 
     double lp_new;
     if constexpr (EPL == 8) {
-      // ---------------- register path: this lane's elements are [8 g, 8 g + 8) ----------------
+      // ------- register path: this lane's elements are {2 (g + G k), 2 (g + G k) + 1}, k = 0..3 -------
       auto ld8 = [&](const double* row, double (&v)[8]) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const double2 t2 = *reinterpret_cast<const double2*>(row + 8 * g + 2 * k);
+          const double2 t2 = *reinterpret_cast<const double2*>(row + 2 * (g + G * k));
           v[2 * k] = t2.x;
           v[2 * k + 1] = t2.y;
         }
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k)  // the proposal replaces the own row: source of the bulk store
-        *reinterpret_cast<double2*>(s + 8 * g + 2 * k) = make_double2(q[2 * k], q[2 * k + 1]);
+        *reinterpret_cast<double2*>(s + 2 * (g + G * k)) = make_double2(q[2 * k], q[2 * k + 1]);
       // red_blue.py:93 -> ensemble.py:458-553: the registered models on registers (lane-sequential partial sums,
       // then the xor-shuffle reduction over the walker's lanes: the order depends only on ndim)
       double acc = 0.0;
@@ -273,14 +274,22 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
           const double d = sqrt(acc) - a.model.s0;
           lp_new = -(d * d) / (2.0 * a.model.s1 * a.model.s1);
         }
-      } else {  // EB_MODEL_ROSENBROCK: the successor of this lane's last element lives in the next lane
-        const double nxt = __shfl_down_sync(mask, q[0], 1);
+      } else {  // EB_MODEL_ROSENBROCK: x[e+1] of a chunk's second element is the next chunk's first element
+        const int first = lane & ~(G - 1);  // first lane of this walker's group
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const double x0 = q[e], x1 = e < 7 ? q[e < 7 ? e + 1 : 7] : nxt;
-          const double t1 = x1 - x0 * x0;
-          const double u1 = a.model.s0 - x0;
-          if (e < 7 || g + 1 < G) acc += a.model.s1 * (t1 * t1) + u1 * u1;
+        for (int k = 0; k < 4; ++k) {
+          const double from_next_lane = __shfl_down_sync(mask, q[2 * k], 1);            // chunk g + 1 + G k
+          const double from_first_lane = __shfl_sync(mask, q[k < 3 ? 2 * k + 2 : 0], first);  // chunk G (k + 1)
+          const double x0 = q[2 * k], x1 = q[2 * k + 1];
+          const double x2 = (g + 1 < G) ? from_next_lane : from_first_lane;
+          {
+            const double t1 = x1 - x0 * x0, u1 = a.model.s0 - x0;
+            acc += a.model.s1 * (t1 * t1) + u1 * u1;
+          }
+          if (k < 3 || g + 1 < G) {  // (element ndim - 1 has no successor)
+            const double t1 = x2 - x1 * x1, u1 = a.model.s0 - x1;
+            acc += a.model.s1 * (t1 * t1) + u1 * u1;
+          }
         }
         lp_new = -group_sum(acc, G, mask);
       }
