@@ -521,13 +521,16 @@ def rooflines(args, w, value_per_gpu, fp64_peak, fp64_src):
 def other_configs(args, dist):
     world = dist.world
     specs = [
-        ("config1 gauss_iso 32x5 stretch (quickstart shape)", "gauss_iso", 32 * world if world > 1 else 32, 5),
-        ("config2 gauss_dense 4096x128 stretch", "gauss_dense", 4096, 128),
         ("config4 rosenbrock 16384x256 0.8 DE + 0.2 snooker", "rosenbrock", 16384, 256),
         ("config5 ring %dx32 stretch%s" % (262144 if world == 1 else 32768 * world,
                                            "" if world == 1 else " (weak: 32768 per GPU)"),
          "ring", 262144 if world == 1 else 32768 * world, 32),
     ]
+    if world == 1:  # the single-GPU configurations of BASELINE.json
+        specs = [
+            ("config1 gauss_iso 32x5 stretch (quickstart shape)", "gauss_iso", 32, 5),
+            ("config2 gauss_dense 4096x128 stretch", "gauss_dense", 4096, 128),
+        ] + specs
     out = {}
     for label, name, n, d in specs:
         try:
