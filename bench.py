@@ -398,6 +398,8 @@ def build_sampler(args, w, dist, gather_results=True, pinned=False):
         eng.set_option("dmma_stagger", 0)
     if args.no_pdl:
         eng.set_option("pdl", 0)
+    if args.no_own_reg:
+        eng.set_option("tma_own_reg", 0)
     return s
 
 
@@ -639,6 +641,7 @@ def main():
                     help="do not launch the fp64 peak micro-benchmarks (for ncu launch lists); use the recorded peak")
     ap.add_argument("--tma-rows", type=int, default=0, help="tma_rows option value (1: short rows only, 2: long rows too)")
     ap.add_argument("--no-tma-rows", action="store_true", help="HBM-bound models: use the generic kernel instead of tma_rows")
+    ap.add_argument("--no-own-reg", action="store_true", help="tma_rows: stage the own rows through the TMA unit as well")
     ap.add_argument("--no-stagger", action="store_true", help="dense_dmma: all pairs request their first tile at once")
     ap.add_argument("--no-pdl", action="store_true", help="dense_dmma: plain stream-ordered launches instead of programmatic dependent launches")
     ap.add_argument("--dmma-group", type=int, default=0, help="half-steps per persistent dense_dmma launch (0: library default)")

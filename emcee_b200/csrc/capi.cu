@@ -76,6 +76,7 @@ struct eb_ctx {
   const char* last_kernel = "none";
   bool allow_dmma = true;
   int allow_tma = 2;  // TMA row-gather kernel for the HBM-bound models: 0 off, 1 short rows only, 2 long rows too
+  bool tma_own_reg = true;  // tma_rows, stretch rows <= 512 B: own rows through registers instead of the TMA unit
   bool fused_last = false;  // the last dense_dmma launch carried the P2P barrier itself
   int dmma_stagger = 1;
   int dmma_group = 1;  // half-steps per persistent dense_dmma launch (1: a launch per half-step)
@@ -738,7 +739,7 @@ int launch_step_generic(eb_ctx* c, const eb_move& mv, uint64_t step, const int32
     c->chain_ok = false;
     bool used_tma = false;
     if (c->allow_tma && !c->debug)
-      CK(c, launch_half_step_tma(mv.kind, a, c->sm_count, c->allow_tma >= 2, c->st, &used_tma));
+      CK(c, launch_half_step_tma(mv.kind, a, c->sm_count, c->allow_tma >= 2, c->tma_own_reg, c->st, &used_tma));
     if (used_tma) {
       c->last_kernel = "tma_rows";
     } else {
@@ -1428,6 +1429,10 @@ int eb_set_option(eb_ctx* c, const char* name, int64_t value) {
   if (!strcmp(name, "dmma_group")) {
     if (value < 1) FAIL(c, EB_ERR_INVALID, "dmma_group must be >= 1");
     c->dmma_group = (int)std::min<int64_t>(value, 1 << 20);
+    return EB_OK;
+  }
+  if (!strcmp(name, "tma_own_reg")) {
+    c->tma_own_reg = value != 0;
     return EB_OK;
   }
   if (!strcmp(name, "dmma_local_first")) {

@@ -96,9 +96,10 @@ cudaError_t launch_locality_tables(const int32_t* order, const StepInfo* info_de
                                    int front_cap, int32_t* aperm, cudaStream_t st);
 cudaError_t launch_half_step_generic(int move_kind, const HalfStepArgs& a, cudaStream_t st);
 // TMA row-gather variant for the HBM-bound models (tma_rows.cu); *used == false: not applicable, use the generic one
-// (long_rows: also take rows so long that only one walker per tile fits)
-cudaError_t launch_half_step_tma(int move_kind, const HalfStepArgs& a, int sm_count, bool long_rows, cudaStream_t st,
-                                 bool* used);
+// (long_rows: also take rows so long that only one walker per tile fits; own_reg: stretch rows of <= 512 bytes keep
+// the own row in registers -- plain loads / stores -- and stage only the partner rows)
+cudaError_t launch_half_step_tma(int move_kind, const HalfStepArgs& a, int sm_count, bool long_rows, bool own_reg,
+                                 cudaStream_t st, bool* used);
 cudaError_t launch_logprob_generic(const ModelDev& m, const double* x, int64_t rows, int D, double* out,
                                    int* status, cudaStream_t st);
 // specialised: stretch + dense Gaussian on FP64 tensor cores (DMMA).  Returns

@@ -52,9 +52,15 @@ struct WalkerMeta {
 // needs ndim == 8 * lanes per walker, which covers 32-D at 8 walkers per tile, 128-D at 2, 256-D at 1.  Rows
 // are read with 16-byte shared-memory loads into registers; the proposal, the log-probability and the snooker
 // norms run on registers with fully unrolled loops.  EPL == 0: any even ndim, strided elements, run-time loops.
-template <int MOVE, int MODEL, int EPL>
+// OWN_REG (stretch, EPL == 8, rows of at most 512 bytes): the own row never touches shared memory -- it is read
+// with four 16-byte global loads per lane one tile ahead, the proposal lives in registers and an accepted row is
+// stored from them; only the partner rows travel by TMA.  For 256-byte rows the SM's TMA unit is the limiter
+// (ncu: ~100 row copies/us against ~113 for a copy-only probe), and this takes two of the 2.3 row requests per
+// walker-step off it.
+template <int MOVE, int MODEL, int EPL, bool OWN_REG>
 __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const HalfStepArgs a, const int R) {
-  constexpr int NR = RowsPerWalker<MOVE>::value;
+  static_assert(!OWN_REG || (MOVE == EB_MOVE_STRETCH && EPL == 8), "OWN_REG is the stretch register path");
+  constexpr int NR = RowsPerWalker<MOVE>::value - (OWN_REG ? 1 : 0);  // rows per walker staged in shared memory
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D;
   const int G = 32 / R;           // lanes per walker = tiles per batch
@@ -134,8 +140,9 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
     double* buf = wbuf + (size_t)stage * stage_doubles;
     if (lane == 0) mbar_arrive_expect_tx(bars + stage, (unsigned)(NR * R) * row_bytes);
     __syncwarp();
-    // copy c (< NR*R <= 32) is row j = c / R of walker r = c % R; its ids live in lane tb * R + r
-    const int c = lane, j = c / R, r = c % R;
+    // copy c (< NR*R <= 32) is row j = c / R (+1 when the own row is not staged) of walker r = c % R; its ids
+    // live in lane tb * R + r
+    const int c = lane, j = c / R + (OWN_REG ? 1 : 0), r = c % R;
     const int src = (tb * R + r) & 31;
     const int wself = m.w >= 0 ? m.w : -(m.w + 1);
     const int src_self = __shfl_sync(0xffffffffu, wself, src);
@@ -145,15 +152,28 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
     if (c < NR * R) {
       const int64_t wr = j == 0 ? src_self : (j == 1 ? src_p0 : (j == 2 ? src_p1 : src_p2));
       const double* srcp = (j == 0) ? a.coords + (size_t)wr * D : row_ptr(a, wr);
-      bulk_g2s(buf + ((size_t)j * R + r) * RS, srcp, row_bytes, bars + stage);
+      bulk_g2s(buf + ((size_t)(j - (OWN_REG ? 1 : 0)) * R + r) * RS, srcp, row_bytes, bars + stage);
+    }
+  };
+  // OWN_REG: this lane's four 16-byte chunks of the own row of its group's walker in tile tb of a batch
+  auto load_own = [&](const WalkerMeta& m, int tb, double (&v)[8]) {
+    const int wsrc = __shfl_sync(0xffffffffu, m.w >= 0 ? m.w : -(m.w + 1), (tb * R + grp) & 31);
+    const double* row = a.coords + (size_t)wsrc * D;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const double2 t2 = __ldcg(reinterpret_cast<const double2*>(row + 2 * (g + G * kk)));
+      v[2 * kk] = t2.x;
+      v[2 * kk + 1] = t2.y;
     }
   };
 
   // this warp's k-th tile is tile_first + k * tstride; tiles come in batches of G (one walker per lane)
   WalkerMeta batch{}, batch_next{};
+  double own_cur[8], own_next[8];  // OWN_REG: own rows of this tile / the next one
   if (tile_first < ntiles) {
     batch = prep_batch(0);
     issue(batch, 0, 0);
+    if (OWN_REG) load_own(batch, 0, own_cur);
   }
   unsigned k = 0;
   for (int64_t tile = tile_first; tile < ntiles; tile += tstride, ++k) {
@@ -164,12 +184,15 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
     if (has_next) {
       const bool crosses = tb + 1 == G;  // the next tile opens a new batch: tabulate it first
       if (crosses) batch_next = prep_batch((int64_t)(k + 1) / G);
-      bulk_wait_read();  // the accepted rows of tile k-1 have left the other stage
+      if (!OWN_REG) bulk_wait_read();  // the accepted rows of tile k-1 have left the other stage
       __syncwarp();
-      if (crosses)
+      if (crosses) {
         issue(batch_next, 0, stage ^ 1);
-      else
+        if (OWN_REG) load_own(batch_next, 0, own_next);
+      } else {
         issue(batch, tb + 1, stage ^ 1);
+        if (OWN_REG) load_own(batch, tb + 1, own_next);
+      }
     }
     // this group's walker: scalars from the lane that tabulated it
     const int me = (tb * R + grp) & 31;
@@ -180,12 +203,13 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
     const double cur_lp_old = __shfl_sync(0xffffffffu, batch.lp_old, me);
     mbar_wait(bars + stage, (k >> 1) & 1u);
 
-    double* s = buf + ((size_t)0 * R + grp) * RS;  // own row, overwritten by the proposal
+    double* s = buf + ((size_t)0 * R + grp) * RS;  // own row, overwritten by the proposal (unused with OWN_REG)
     const bool valid = cur_w >= 0;
     const int64_t w = valid ? cur_w : -(cur_w + 1);
     double factor = cur_factor;
 
     double lp_new;
+    double q_keep[8];  // OWN_REG: the proposal, kept for the store of an accepted row
     if constexpr (EPL == 8) {
       // ------- register path: this lane's elements are {2 (g + G k), 2 (g + G k) + 1}, k = 0..3 -------
       auto ld8 = [&](const double* row, double (&v)[8]) {
@@ -199,8 +223,14 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
       double q[8];
       if (MOVE == EB_MOVE_STRETCH) {
         double sv[8], cv[8];
-        ld8(s, sv);
-        ld8(buf + ((size_t)1 * R + grp) * RS, cv);
+        if (OWN_REG) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sv[e] = own_cur[e];
+          ld8(buf + (size_t)grp * RS, cv);  // the only staged row of this walker
+        } else {
+          ld8(s, sv);
+          ld8(buf + ((size_t)1 * R + grp) * RS, cv);
+        }
         const double zz = cur_scalar;
 #pragma unroll
         for (int e = 0; e < 8; ++e)  // stretch.py:33  q = c - (c - s) * zz   (each op rounded once)
@@ -251,6 +281,10 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
         const double qn = sqrt(group_sum(m2, G, mask));
         factor = __dmul_rn((double)D - 1.0, __dsub_rn(log(qn), log(norm)));  // de_snooker.py:45-46
       }
+      if (OWN_REG) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) q_keep[e] = q[e];
+      }
       bool bad = false;
 #pragma unroll
       for (int e = 0; e < 8; ++e) bad |= !isfinite(q[e]);
@@ -258,9 +292,11 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
 #pragma unroll
         for (int e = 0; e < 8; ++e) flag_nonfinite(q[e], a.status);  // ensemble.py:476-479
       }
+      if (!OWN_REG) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)  // the proposal replaces the own row: source of the bulk store
-        *reinterpret_cast<double2*>(s + 2 * (g + G * k)) = make_double2(q[2 * k], q[2 * k + 1]);
+        for (int k = 0; k < 4; ++k)  // the proposal replaces the own row: source of the bulk store
+          *reinterpret_cast<double2*>(s + 2 * (g + G * k)) = make_double2(q[2 * k], q[2 * k + 1]);
+      }
       // red_blue.py:93 -> ensemble.py:458-553: the registered models on registers (lane-sequential partial sums,
       // then the xor-shuffle reduction over the walker's lanes: the order depends only on ndim)
       double acc = 0.0;
@@ -355,18 +391,38 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
     // red_blue.py:96-101
     const double lnpdiff = __dsub_rn(__dadd_rn(factor, lp_new), cur_lp_old);
     const bool acc = valid && (lnpdiff > cur_log_u);
-    // red_blue.py:103-104 -> move.py:29-34: one bulk store per accepted row
-    fence_async_smem();
-    __syncwarp();
-    if (g == 0) {
+    if constexpr (OWN_REG) {
+      // red_blue.py:103-104 -> move.py:29-34: an accepted row is stored from the registers that hold the proposal
       if (acc) {
-        bulk_s2g(a.coords + (size_t)w * D, s, row_bytes);
-        a.logp[w] = lp_new;
-        atomicAdd(a.nacc + w, 1ull);
+        double* dst = a.coords + (size_t)w * D;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          *reinterpret_cast<double2*>(dst + 2 * (g + G * kk)) = make_double2(q_keep[2 * kk], q_keep[2 * kk + 1]);
       }
-      if (valid) a.accepted[w] = acc ? 1 : 0;
+      if (g == 0) {
+        if (acc) {
+          a.logp[w] = lp_new;
+          atomicAdd(a.nacc + w, 1ull);
+        }
+        if (valid) a.accepted[w] = acc ? 1 : 0;
+      }
+      __syncwarp();  // every lane is done reading this stage before the next iteration refills it
+#pragma unroll
+      for (int e = 0; e < 8; ++e) own_cur[e] = own_next[e];
+    } else {
+      // red_blue.py:103-104 -> move.py:29-34: one bulk store per accepted row
+      fence_async_smem();
+      __syncwarp();
+      if (g == 0) {
+        if (acc) {
+          bulk_s2g(a.coords + (size_t)w * D, s, row_bytes);
+          a.logp[w] = lp_new;
+          atomicAdd(a.nacc + w, 1ull);
+        }
+        if (valid) a.accepted[w] = acc ? 1 : 0;
+      }
+      bulk_commit();
     }
-    bulk_commit();
     if (tb + 1 == G) batch = batch_next;
   }
   // every accepted row has left shared memory AND reached global memory before the warp retires
@@ -374,7 +430,8 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
 }
 
 template <int MOVE, int MODEL>
-cudaError_t launch_tma_t(const HalfStepArgs& a, int sm_count, bool long_rows, cudaStream_t st, bool* used) {
+cudaError_t launch_tma_t(const HalfStepArgs& a, int sm_count, bool long_rows, bool own_rows_in_registers, cudaStream_t st,
+                         bool* used) {
   constexpr int NR = RowsPerWalker<MOVE>::value;
   *used = false;
   const int D = a.D;
@@ -400,14 +457,21 @@ cudaError_t launch_tma_t(const HalfStepArgs& a, int sm_count, bool long_rows, cu
     }
   }
   if (R == 0) return cudaSuccess;  // generic kernel
-  const size_t smem = (size_t)nwarps * warp_bytes(R) + (size_t)nwarps * 2 * sizeof(uint64_t);
+  const bool epl8 = D == 8 * (32 / R);  // 8 elements per lane: the register path
+  // short rows (<= 512 B) of the stretch move: own rows by plain loads, only the partner rows on the TMA unit
+  const bool own_reg = MOVE == EB_MOVE_STRETCH && epl8 && D <= 64 && own_rows_in_registers;
+  const int nr_smem = NR - (own_reg ? 1 : 0);
+  const size_t smem = (size_t)nwarps * warp_bytes(R) / NR * nr_smem + (size_t)nwarps * 2 * sizeof(uint64_t);
   const int64_t count = (int64_t)a.i_hi - a.i_lo;
   if (count <= 0) {
     *used = true;
     return cudaSuccess;
   }
-  const bool epl8 = D == 8 * (32 / R);  // 8 contiguous elements per lane: the register path
-  auto kern = epl8 ? half_step_tma_kernel<MOVE, MODEL, 8> : half_step_tma_kernel<MOVE, MODEL, 0>;
+  void (*kern)(const HalfStepArgs, const int) =
+      epl8 ? half_step_tma_kernel<MOVE, MODEL, 8, false> : half_step_tma_kernel<MOVE, MODEL, 0, false>;
+  if constexpr (MOVE == EB_MOVE_STRETCH) {
+    if (own_reg) kern = half_step_tma_kernel<MOVE, MODEL, 8, true>;
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t ntiles = (count + R - 1) / R;
@@ -419,14 +483,14 @@ cudaError_t launch_tma_t(const HalfStepArgs& a, int sm_count, bool long_rows, cu
 }
 
 template <int MOVE>
-cudaError_t launch_tma_m(const HalfStepArgs& a, int sm_count, bool long_rows, cudaStream_t st, bool* used) {
+cudaError_t launch_tma_m(const HalfStepArgs& a, int sm_count, bool long_rows, bool own_reg, cudaStream_t st, bool* used) {
   switch (a.model.kind) {
     case EB_MODEL_GAUSS_ISO:
-      return launch_tma_t<MOVE, EB_MODEL_GAUSS_ISO>(a, sm_count, long_rows, st, used);
+      return launch_tma_t<MOVE, EB_MODEL_GAUSS_ISO>(a, sm_count, long_rows, own_reg, st, used);
     case EB_MODEL_ROSENBROCK:
-      return launch_tma_t<MOVE, EB_MODEL_ROSENBROCK>(a, sm_count, long_rows, st, used);
+      return launch_tma_t<MOVE, EB_MODEL_ROSENBROCK>(a, sm_count, long_rows, own_reg, st, used);
     case EB_MODEL_RING:
-      return launch_tma_t<MOVE, EB_MODEL_RING>(a, sm_count, long_rows, st, used);
+      return launch_tma_t<MOVE, EB_MODEL_RING>(a, sm_count, long_rows, own_reg, st, used);
   }
   *used = false;  // dense Gaussian outside the DMMA envelope: CUDA-core generic kernel
   return cudaSuccess;
@@ -436,15 +500,15 @@ cudaError_t launch_tma_m(const HalfStepArgs& a, int sm_count, bool long_rows, cu
 
 // Tries the TMA row-gather kernel; *used tells whether it took the half-step (otherwise the
 // caller falls back to half_step_generic_kernel).
-cudaError_t launch_half_step_tma(int move_kind, const HalfStepArgs& a, int sm_count, bool long_rows, cudaStream_t st,
-                                 bool* used) {
+cudaError_t launch_half_step_tma(int move_kind, const HalfStepArgs& a, int sm_count, bool long_rows, bool own_reg,
+                                 cudaStream_t st, bool* used) {
   switch (move_kind) {
     case EB_MOVE_STRETCH:
-      return launch_tma_m<EB_MOVE_STRETCH>(a, sm_count, long_rows, st, used);
+      return launch_tma_m<EB_MOVE_STRETCH>(a, sm_count, long_rows, own_reg, st, used);
     case EB_MOVE_DE:
-      return launch_tma_m<EB_MOVE_DE>(a, sm_count, long_rows, st, used);
+      return launch_tma_m<EB_MOVE_DE>(a, sm_count, long_rows, own_reg, st, used);
     case EB_MOVE_SNOOKER:
-      return launch_tma_m<EB_MOVE_SNOOKER>(a, sm_count, long_rows, st, used);
+      return launch_tma_m<EB_MOVE_SNOOKER>(a, sm_count, long_rows, own_reg, st, used);
   }
   *used = false;
   return cudaErrorInvalidValue;
