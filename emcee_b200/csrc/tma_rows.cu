@@ -17,9 +17,9 @@
 // G tiles (= 32 walkers) every lane does it for ONE walker, and the tile loop fetches what it needs with
 // shuffles -- at 32-D that removes three quarters of the kernel's instructions (ncu: 964 -> ~500 per tile).
 //
-// Layout of a stage: [NR][R][D + G] doubles -- NR rows per walker (own + partners), R walkers
-// per tile, G = 32 / R lanes per walker; the G-double pad staggers consecutive walkers' rows
-// across the banks so a warp-wide access costs the minimum two wavefronts.
+// Layout of a stage: [NR][R][D + pad] doubles -- NR rows per walker (own + partners), R walkers
+// per tile, G = 32 / R lanes per walker; the pad (G doubles, 2 G on the register path) staggers consecutive
+// walkers' rows across the banks so a warp-wide access costs the minimum number of wavefronts.
 #include <math.h>
 
 #include "engine.cuh"
@@ -64,7 +64,9 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1) half_step_tma_kernel(const
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D;
   const int G = 32 / R;           // lanes per walker = tiles per batch
-  const int RS = D + G;           // padded row stride (doubles)
+  // padded row stride (doubles): consecutive walkers' rows are staggered across the banks -- by G doubles for the
+  // strided 8-byte accesses of the run-time path, by 2 G for the 16-byte chunks of the register path
+  const int RS = D + (EPL == 8 ? 2 * G : G);
   const int stage_doubles = NR * R * RS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarps = blockDim.x >> 5;
@@ -440,7 +442,10 @@ cudaError_t launch_tma_t(const HalfStepArgs& a, int sm_count, bool long_rows, bo
   // walkers per tile R = the largest power of two with NR*R <= 32 copies per stage that fits.  Rows so long
   // that only one walker per tile fits (e.g. 256-D DE / snooker) run with R = 1 and as many warps (>= 8) as
   // 200 KB hold -- `long_rows`; measured against the generic kernel in profiles/r02_hbm_kernels.md.
-  auto warp_bytes = [&](int r) { return (size_t)2 * NR * r * (D + 32 / r) * sizeof(double); };
+  auto warp_bytes = [&](int r) {
+    const int pad = (D == 8 * (32 / r)) ? 2 * (32 / r) : 32 / r;  // the kernel's row stride (register path: 2 G)
+    return (size_t)2 * NR * r * (D + pad) * sizeof(double);
+  };
   int nwarps = 16;
   const size_t budget = (size_t)192 * 1024 / nwarps;
   int R = 0;
