@@ -81,7 +81,7 @@ struct eb_ctx {
   int dmma_stagger = 1;
   int dmma_group = 1;  // half-steps per persistent dense_dmma launch (1: a launch per half-step)
   int pdl = 1;           // dense_dmma launches chain as programmatic dependents (1: one GPU only, 2: sharded too)
-  int local_first = 1;  // sharded dense_dmma: local-partner tiles first, peer barrier behind them (0 never, 1 auto, 2 always)
+  int local_first = 0;  // sharded dense_dmma: local-partner tiles first, peer barrier behind them (0 never, 1 auto, 2 always)
   bool chain_ok = false; // the last operation enqueued on the stream is a dense_dmma kernel of this run
   // multi-GPU: log_prob / accept mask / counters (and, P2P, coords) of rows owned by OTHER ranks are stale
   // on this rank until the next collective read (eb_get_state, eb_get_naccepted, ...) replicates them
@@ -871,8 +871,9 @@ int flush_dmma(eb_ctx* c, const eb_move& mv, DmmaGroup& grp, uint64_t& launches)
   int bound = grp.max_count;
   if (c->comm.nranks > 1 && c->comm.rows_per_rank < bound) bound = (int)c->comm.rows_per_rank;
   // Locality-sorted tiles hide the peer barrier and the first remote fetch behind local work, but move the
-  // remote burst to the second round: measured (profiles/r02_ab_2gpu.md) a gain when a consumer warp has
-  // at most ~2 tiles per half-step (strong scaling: +4 %) and a loss with long tile lists (weak: -4 %).
+  // remote burst to the second round: measured (profiles/r02_ab_2gpu.md) +4 % for strong scaling on 2 GPUs,
+  // -4 % for weak scaling on 2 GPUs and -6 % for strong scaling on 4 GPUs -- hence off by default; "auto"
+  // (option value 1) enables it when a consumer warp has at most ~2 tiles per half-step.
   const bool few_tiles = (bound + 7) / 8 <= 2 * DMMA_TILE_SLOTS * c->sm_count;
   a.aperm = (c->comm.nranks > 1 && (c->local_first == 2 || (c->local_first == 1 && few_tiles))) ? c->comm.aperm : nullptr;
   // P2P: the peer barrier rides inside the kernel (wait at its start, between its half-steps, signal at its end)

@@ -217,8 +217,8 @@ int eb_debug_timeline(eb_ctx* ctx, int64_t* out, size_t capacity, size_t* writte
  * in-kernel grid barrier -- and, on a P2P-sharded ensemble, a peer-flag barrier; default 1), "pdl" (0/1/2: consecutive dense_dmma launches chain as programmatic
  * dependent launches so a launch's prologue overlaps its predecessor's tail; 1 = on one GPU (default), 2 = on sharded ensembles too), "tma_own_reg" (0/1: tma_rows with the stretch move and rows of at most 512 bytes keeps the own row
  * in registers and stages only the partner rows; default 1), "dmma_local_first" (0/1/2: sharded dense_dmma -- build the first round of tiles from walkers whose
- * partner is local and take the peer barrier behind them; 0 never, 1 when a consumer warp has at most two tiles per half-step
- * (default), 2 always), "moments_every" (n >= 0: see
+ * partner is local and take the peer barrier behind them; 0 never (default: the measured effect changes sign with the
+ * number of GPUs), 1 when a consumer warp has at most two tiles per half-step, 2 always), "moments_every" (n >= 0: see
  * eb_moments; setting it resets the accumulators), "dmma_timeline" (0/1: record consumer cycle stamps
  * for eb_debug_timeline), "l2_flush"
  * (0/1: benchmark hygiene -- write a 256 MiB buffer before every step and time
