@@ -267,7 +267,12 @@ class EnsembleSampler(object):
         _bulk=False,
     ):
         """Advance the chain as a generator (``ensemble.py:258-424``): yields the
-        live :class:`State` every ``thin_by`` steps."""
+        live :class:`State` every ``thin_by`` steps.
+
+        Device-detected errors (NaN log-probability, non-finite proposal -- the
+        reference's ``ValueError`` s, ``ensemble.py:476-479,550-551``) are raised
+        when the C-ABI call that contains the offending step returns: per yielded
+        state here, after the whole run for :meth:`run_mcmc` (one call)."""
         if log_prob0 is not None or rstate0 is not None or blobs0 is not None:
             raise NotImplementedError("log_prob0/rstate0/blobs0 are deprecated in the reference; pass a State")
         pbar = None
